@@ -1,0 +1,124 @@
+/* tlpb200.h -- C ABI of the B200-native KKT backend for Tulip.jl's IPM.
+ *
+ * The reference has no FFI: its KKT plug-in boundary is Julia multiple dispatch
+ * (/root/reference/src/KKT/KKT.jl:59 setup, :83 update!, :100 solve!, :114 backend,
+ * :121 linear_system).  Each entry point below is what a Julia `ccall` (see
+ * tulip.jl_b200/julia/TlpB200.jl and INTEGRATION.md) binds to implement one of those methods
+ * for a new `TlpB200.Backend <: AbstractKKTBackend`.
+ *
+ * Conventions
+ *   - A is CSC: colptr[n+1], rowval[nnz], nzval[nnz]; 64-bit indices as in Julia's
+ *     SparseMatrixCSC{Float64,Int} (src/LinearAlgebra/LinearAlgebra.jl:16-32); `index_base`
+ *     is 1 when called from Julia, 0 from C/Python.
+ *   - All vectors are Float64.  Host-pointer calls copy in/out through pinned staging inside the
+ *     library and are fully synchronised on return (results are read on the host right away,
+ *     src/IPM/HSD/step.jl:225-237).  `_dev` variants take device pointers and only enqueue work
+ *     on the solver's stream.
+ *   - theta_inv / regP / regD are copied on entry (src/KKT/Cholmod/spd.jl:36-38); xi_p, xi_d are
+ *     read-only (the caller passes dat.b itself, src/IPM/HSD/step.jl:63).
+ *   - No CPU fallback: every numeric entry point fails with TLPB200_CUDA if no sm_100 device
+ *     is usable.
+ */
+#ifndef TLPB200_H
+#define TLPB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tlpb200_solver tlpb200_solver; /* opaque */
+
+enum {
+    TLPB200_OK = 0,
+    TLPB200_NOT_POSDEF = 1, /* wrong-sign / zero / NaN pivot -> Julia PosDefException (spd.jl:47, ldlfact.jl:115) */
+    TLPB200_OOM = 2,        /* host or device allocation failed -> Julia OutOfMemoryError (HSD.jl:327) */
+    TLPB200_BAD_ARG = 3,    /* dimension / argument error -> Julia DimensionMismatch (spd.jl:26-34) */
+    TLPB200_CUDA = 4,       /* CUDA runtime error or no usable device -> ErrorException */
+    TLPB200_INTERNAL = 5
+};
+
+enum { TLPB200_K1 = 1, TLPB200_K2 = 2 }; /* src/KKT/systems.jl:32 (K2), :54 (K1) */
+
+typedef struct tlpb200_options {
+    int32_t ordering;      /* 0 natural, 1 approximate minimum degree (default 1) */
+    int32_t device;        /* CUDA device ordinal (default 0) */
+    int32_t piece_width;   /* column-piece width for wide supernodes (default 128; multiple of 64) */
+    int32_t small_elems;   /* supernodes with nrow*ncol <= this run in the one-CTA kernels (default 4096) */
+    int32_t relax_always;  /* amalgamation: always merge when merged width <= this (default 8) */
+    int32_t use_graph;     /* 1 = replay update!/solve! as CUDA graphs (default 1) */
+    int32_t analyze_only;  /* 1 = host symbolic analysis only, no device is touched (tests, no GPU) */
+    int32_t reserved[9];
+} tlpb200_options;
+
+typedef struct tlpb200_stats {
+    int64_t m, n, nnzA;
+    int64_t order;          /* N: m for K1, n+m for K2 */
+    int64_t nnzL;           /* sum of column counts (structural, before amalgamation) */
+    int64_t nnzL_stored;    /* doubles of panel storage on the device */
+    double flops;           /* sum of squared column counts = factorisation flops */
+    int64_t nsuper, npieces, nlevels;
+    int64_t max_ncol, max_nrow;
+    int64_t nproducts;      /* K1: scalar products a_ij*a_kj streamed by the assemble kernel */
+    int64_t nentries;       /* K1: structural non-zeros of lower(A*A') */
+    int64_t launches_update, launches_solve; /* kernels of one update! / one solve! */
+    double ms_assemble, ms_factor, ms_solve;  /* CUDA-event times of the last update!/solve! (profiling mode) */
+    int64_t bad_pivot;      /* permuted column of the first bad pivot of the last update!, -1 if none */
+    int64_t n_update, n_solve;
+    int64_t bytes_device;
+} tlpb200_stats;
+
+void tlpb200_default_options(tlpb200_options* opt);
+
+/* KKT.setup(A, system, backend)  (KKT.jl:59; Cholmod/spd.jl:5-20, sqd.jl:5-22):
+ * symbolic analysis on the host, plan + matrix upload to the device. */
+int tlpb200_create(tlpb200_solver** out, int64_t m, int64_t n, const int64_t* colptr, const int64_t* rowval,
+                   const double* nzval, int index_base, int system, const tlpb200_options* opt);
+
+/* KKT.update!(kkt, theta_inv, regP, regD)  (KKT.jl:83; spd.jl:22-50, sqd.jl:24-55):
+ * assemble + numeric factorisation on the device.  *bad_pivot (may be NULL) receives the
+ * permuted column index of the first bad pivot or -1. */
+int tlpb200_update(tlpb200_solver* s, const double* theta_inv, const double* regP, const double* regD,
+                   int64_t* bad_pivot);
+int tlpb200_update_dev(tlpb200_solver* s, const double* d_theta_inv, const double* d_regP, const double* d_regD);
+/* result of the last update_dev: synchronises, returns TLPB200_OK / TLPB200_NOT_POSDEF */
+int tlpb200_update_status(tlpb200_solver* s, int64_t* bad_pivot);
+
+/* KKT.solve!(dx, dy, kkt, xi_p, xi_d)  (KKT.jl:100; spd.jl:52-70, sqd.jl:57-74).
+ * nrhs right-hand sides stored with leading dimensions ldx (dx, xi_d) and ldy (dy, xi_p). */
+int tlpb200_solve(tlpb200_solver* s, double* dx, double* dy, const double* xi_p, const double* xi_d,
+                  int32_t nrhs, int64_t ldx, int64_t ldy);
+int tlpb200_solve_dev(tlpb200_solver* s, double* d_dx, double* d_dy, const double* d_xi_p, const double* d_xi_d,
+                      int32_t nrhs, int64_t ldx, int64_t ldy);
+
+/* stream the _dev calls enqueue on (a cudaStream_t); default: a stream owned by the solver */
+int tlpb200_set_stream(tlpb200_solver* s, void* cuda_stream);
+int tlpb200_synchronize(tlpb200_solver* s);
+/* 1 = bracket assemble / factor / solve with CUDA events and fill ms_* in the stats (adds syncs) */
+int tlpb200_set_profiling(tlpb200_solver* s, int on);
+
+int tlpb200_stats_get(const tlpb200_solver* s, tlpb200_stats* out);
+
+/* Integer results of the symbolic analysis, for the bit-exact tests.  Each pointer may be NULL.
+ * perm[N] (perm[new]=old, 0-based), parent[N] (etree of the permuted matrix, -1 root),
+ * colcount[N], sn_first[nsuper+1]. */
+int tlpb200_get_symbolic(const tlpb200_solver* s, int32_t* perm, int32_t* parent, int32_t* colcount,
+                         int32_t* sn_first);
+/* supernodal row structure: rowptr[nsuper+1], rows[rowptr[nsuper]] (pass NULL to query sizes via stats) */
+int tlpb200_get_structure(const tlpb200_solver* s, int64_t* rowptr, int32_t* rows);
+
+/* Debug/parity: copy the assembled-and-factored panels (or, with factor=0 in the last
+ * tlpb200_debug_assemble call, the assembled matrix) back to the host: Lx[nnzL_stored]. */
+int tlpb200_debug_assemble(tlpb200_solver* s, const double* theta_inv, const double* regP, const double* regD);
+int tlpb200_debug_get_lx(tlpb200_solver* s, double* lx, int64_t* xptr /* nsuper+1, may be NULL */);
+
+const char* tlpb200_last_error(const tlpb200_solver* s);
+const char* tlpb200_backend_name(void);            /* KKT.backend(kkt)       (KKT.jl:114) */
+const char* tlpb200_linear_system(const tlpb200_solver* s); /* KKT.linear_system(kkt) (KKT.jl:121) */
+void tlpb200_destroy(tlpb200_solver* s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TLPB200_H */

@@ -1,0 +1,96 @@
+"""ctypes binding of libtlpb200.so (the C ABI declared in include/tlpb200.h).
+
+This is the Python twin of the Julia ``ccall`` glue in ``julia/TlpB200.jl``: it exists because
+the container has no Julia runtime, so the parity tests and the benchmark drive the very same
+shared library from Python.  There is NO fallback: a missing library raises ImportError, a
+missing device raises ``TlpB200Error`` from the first numeric call.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtlpb200.so")
+
+OK, NOT_POSDEF, OOM, BAD_ARG, CUDA, INTERNAL = 0, 1, 2, 3, 4, 5
+K1, K2 = 1, 2
+
+
+class Options(C.Structure):
+    _fields_ = [("ordering", C.c_int32), ("device", C.c_int32), ("piece_width", C.c_int32),
+                ("small_elems", C.c_int32), ("relax_always", C.c_int32), ("use_graph", C.c_int32),
+                ("analyze_only", C.c_int32), ("reserved", C.c_int32 * 9)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("m", C.c_int64), ("n", C.c_int64), ("nnzA", C.c_int64), ("order", C.c_int64),
+                ("nnzL", C.c_int64), ("nnzL_stored", C.c_int64), ("flops", C.c_double),
+                ("nsuper", C.c_int64), ("npieces", C.c_int64), ("nlevels", C.c_int64),
+                ("max_ncol", C.c_int64), ("max_nrow", C.c_int64),
+                ("nproducts", C.c_int64), ("nentries", C.c_int64),
+                ("launches_update", C.c_int64), ("launches_solve", C.c_int64),
+                ("ms_assemble", C.c_double), ("ms_factor", C.c_double), ("ms_solve", C.c_double),
+                ("bad_pivot", C.c_int64), ("n_update", C.c_int64), ("n_solve", C.c_int64),
+                ("bytes_device", C.c_int64)]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+# every symbol include/tlpb200.h declares (tests check that the library exports all of them)
+SYMBOLS = [
+    "tlpb200_default_options", "tlpb200_create", "tlpb200_update", "tlpb200_update_dev",
+    "tlpb200_update_status", "tlpb200_solve", "tlpb200_solve_dev", "tlpb200_set_stream",
+    "tlpb200_synchronize", "tlpb200_set_profiling", "tlpb200_stats_get", "tlpb200_get_symbolic",
+    "tlpb200_get_structure", "tlpb200_debug_assemble", "tlpb200_debug_get_lx", "tlpb200_last_error",
+    "tlpb200_backend_name", "tlpb200_linear_system", "tlpb200_destroy",
+]
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once).  Fails loudly if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `make -C tulip.jl_b200/csrc` or "
+            "`python -c 'import __graft_entry__ as g; g.build()'`.  There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    p = C.c_void_p
+    dp = C.POINTER(C.c_double)
+    lib.tlpb200_default_options.argtypes = [C.POINTER(Options)]
+    lib.tlpb200_default_options.restype = None
+    lib.tlpb200_create.argtypes = [C.POINTER(p), C.c_int64, C.c_int64, C.POINTER(C.c_int64),
+                                   C.POINTER(C.c_int64), dp, C.c_int, C.c_int, C.POINTER(Options)]
+    lib.tlpb200_update.argtypes = [p, dp, dp, dp, C.POINTER(C.c_int64)]
+    lib.tlpb200_update_dev.argtypes = [p, p, p, p]
+    lib.tlpb200_update_status.argtypes = [p, C.POINTER(C.c_int64)]
+    lib.tlpb200_solve.argtypes = [p, dp, dp, dp, dp, C.c_int32, C.c_int64, C.c_int64]
+    lib.tlpb200_solve_dev.argtypes = [p, p, p, p, p, C.c_int32, C.c_int64, C.c_int64]
+    lib.tlpb200_set_stream.argtypes = [p, p]
+    lib.tlpb200_synchronize.argtypes = [p]
+    lib.tlpb200_set_profiling.argtypes = [p, C.c_int]
+    lib.tlpb200_stats_get.argtypes = [p, C.POINTER(Stats)]
+    lib.tlpb200_get_symbolic.argtypes = [p, p, p, p, p]
+    lib.tlpb200_get_structure.argtypes = [p, p, p]
+    lib.tlpb200_debug_assemble.argtypes = [p, dp, dp, dp]
+    lib.tlpb200_debug_get_lx.argtypes = [p, dp, C.POINTER(C.c_int64)]
+    lib.tlpb200_last_error.argtypes = [p]
+    lib.tlpb200_last_error.restype = C.c_char_p
+    lib.tlpb200_backend_name.argtypes = []
+    lib.tlpb200_backend_name.restype = C.c_char_p
+    lib.tlpb200_linear_system.argtypes = [p]
+    lib.tlpb200_linear_system.restype = C.c_char_p
+    lib.tlpb200_destroy.argtypes = [p]
+    lib.tlpb200_destroy.restype = None
+    for name in ("tlpb200_create", "tlpb200_update", "tlpb200_update_dev", "tlpb200_update_status",
+                 "tlpb200_solve", "tlpb200_solve_dev", "tlpb200_set_stream", "tlpb200_synchronize",
+                 "tlpb200_set_profiling", "tlpb200_stats_get", "tlpb200_get_symbolic",
+                 "tlpb200_get_structure", "tlpb200_debug_assemble", "tlpb200_debug_get_lx"):
+        getattr(lib, name).restype = C.c_int
+    _lib = lib
+    return lib

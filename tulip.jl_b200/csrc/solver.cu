@@ -1,0 +1,655 @@
+// Host orchestration + C ABI of the B200 KKT backend (see include/tlpb200.h).
+//
+// Mirrors the life-cycle of the reference's CholmodSolver (/root/reference/src/KKT/Cholmod/
+// cholmod.jl:46-60): setup once (spd.jl:5-20 / sqd.jl:5-22), then per IPM iteration one update!
+// (spd.jl:22-50 / sqd.jl:24-55) and 3-6 solve! calls (spd.jl:52-70 / sqd.jl:57-74).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <climits>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/tlpb200.h"
+#include "kernels.cuh"
+#include "plan.hpp"
+#include "symbolic.hpp"
+
+using namespace tlp;
+
+struct tlpb200_solver {
+    tlpb200_options opt;
+    int system = 1;
+    int64_t m = 0, n = 0, nnz = 0;
+    // canonical 0-based CSC copy of A
+    std::vector<int64_t> colptr;
+    std::vector<int32_t> rowidx;
+    std::vector<double> val;
+
+    Symbolic sym;
+    Plan plan;
+    AssemblyMaps maps;
+
+    bool on_device = false;
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::vector<void*> allocs;
+    size_t bytes_device = 0;
+    DevCtx ctx{};
+    DevMat mat{};
+    double *d_theta = nullptr, *d_regP = nullptr, *d_regD = nullptr, *d_d = nullptr;
+    double *d_xip = nullptr, *d_xid = nullptr, *d_dx = nullptr, *d_dy = nullptr;
+    double* h_pin = nullptr;   // pinned staging: 2n + m (update) / (n+m) in + (n+m) out (solve)
+    int32_t* h_info = nullptr; // pinned
+    size_t small_smem = 0;
+
+    cudaGraphExec_t g_update = nullptr, g_solve = nullptr;
+    bool profiling = false;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+
+    int64_t launches_update = 0, launches_solve = 0;
+    double ms_assemble = 0, ms_factor = 0, ms_solve = 0;
+    int64_t bad_pivot = -1, n_update = 0, n_solve = 0;
+    std::string err;
+};
+
+namespace {
+
+struct CudaFail {
+    cudaError_t e;
+    const char* what;
+};
+
+#define CK(call)                                              \
+    do {                                                      \
+        cudaError_t _e = (call);                              \
+        if (_e != cudaSuccess) throw CudaFail{_e, #call};     \
+    } while (0)
+
+template <typename T>
+T* dalloc(tlpb200_solver* s, size_t count) {
+    void* p = nullptr;
+    const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    CK(cudaMalloc(&p, bytes));
+    s->allocs.push_back(p);
+    s->bytes_device += bytes;
+    return (T*)p;
+}
+
+template <typename T>
+const T* upload(tlpb200_solver* s, const std::vector<T>& v) {
+    T* p = dalloc<T>(s, v.size());
+    if (!v.empty()) CK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return p;
+}
+
+int fail(tlpb200_solver* s, int code, const std::string& msg) {
+    if (s) s->err = msg;
+    return code;
+}
+
+int cuda_fail(tlpb200_solver* s, const CudaFail& f) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "CUDA error %d (%s) in %s", (int)f.e, cudaGetErrorString(f.e), f.what);
+    cudaGetLastError();
+    return fail(s, f.e == cudaErrorMemoryAllocation ? TLPB200_OOM : TLPB200_CUDA, buf);
+}
+
+// ---- the numeric phases, enqueued on s->stream; `count` accumulates kernel launches -------------
+void enqueue_assemble(tlpb200_solver* s, int64_t& count) {
+    cudaStream_t st = s->stream;
+    CK(cudaMemsetAsync(s->ctx.Lx, 0, (size_t)s->sym.lx_size * sizeof(double), st));
+    CK(cudaMemsetAsync(s->ctx.info, 0x7f, sizeof(int32_t), st));
+    if (s->system == TLPB200_K1) {
+        launch_compute_d(s->d_theta, s->d_regP, s->d_d, s->n, st);
+        launch_assemble_k1(s->ctx, s->mat, s->d_d, s->d_regD, st);
+        count += 3;
+    } else {
+        launch_assemble_k2(s->ctx, s->mat, s->d_theta, s->d_regP, s->d_regD, st);
+        count += 2;
+    }
+}
+
+void enqueue_factor(tlpb200_solver* s, int64_t& count) {
+    cudaStream_t st = s->stream;
+    for (const LevelPlan& lp : s->plan.levels) {
+        if (lp.small_end > lp.small_begin) {
+            launch_small_factor(s->ctx, lp.small_begin, lp.small_end, s->small_smem, st);
+            count++;
+        }
+        for (int t = 0; t < lp.nsteps; ++t) {
+            if (lp.inner_end[t] > lp.inner_begin[t]) { launch_update(s->ctx, lp.inner_begin[t], lp.inner_end[t], 0, st); count++; }
+            if (lp.panel_end[t] > lp.panel_begin[t]) { launch_trsm(s->ctx, lp.panel_begin[t], lp.panel_end[t], st); count++; }
+        }
+        if (lp.ext_end > lp.ext_begin) { launch_update(s->ctx, lp.ext_begin, lp.ext_end, lp.ext_atomic, st); count++; }
+    }
+    CK(cudaGetLastError());
+}
+
+void enqueue_solve(tlpb200_solver* s, const double* xip, const double* xid, double* dx, double* dy, int64_t& count) {
+    cudaStream_t st = s->stream;
+    if (s->system == TLPB200_K1) launch_k1_rhs(s->ctx, s->mat, s->d_d, xip, xid, st);
+    else launch_k2_rhs(s->ctx, s->mat, xip, xid, st);
+    count++;
+    const auto& L = s->plan.levels;
+    for (size_t l = 0; l < L.size(); ++l) {
+        const LevelPlan& lp = L[l];
+        if (lp.small_end > lp.small_begin) { launch_fwd_small(s->ctx, lp.small_begin, lp.small_end, st); count++; }
+        if (lp.piece_end > lp.piece_begin) { launch_fwd_trsv(s->ctx, lp.piece_begin, lp.piece_end, st); count++; }
+        if (lp.solve_end > lp.solve_begin) { launch_fwd_gemv(s->ctx, lp.solve_begin, lp.solve_end, st); count++; }
+    }
+    for (size_t l = L.size(); l-- > 0;) {
+        const LevelPlan& lp = L[l];
+        if (lp.solve_end > lp.solve_begin) { launch_bwd_gemv(s->ctx, lp.solve_begin, lp.solve_end, st); count++; }
+        if (lp.piece_end > lp.piece_begin) { launch_bwd_trsv(s->ctx, lp.piece_begin, lp.piece_end, st); count++; }
+        if (lp.small_end > lp.small_begin) { launch_bwd_small(s->ctx, lp.small_begin, lp.small_end, st); count++; }
+    }
+    if (s->system == TLPB200_K1) launch_k1_recover(s->ctx, s->mat, s->d_d, xid, dx, dy, st);
+    else launch_k2_recover(s->ctx, s->mat, dx, dy, st);
+    count++;
+    CK(cudaGetLastError());
+}
+
+void destroy_graphs(tlpb200_solver* s) {
+    if (s->g_update) { cudaGraphExecDestroy(s->g_update); s->g_update = nullptr; }
+    if (s->g_solve) { cudaGraphExecDestroy(s->g_solve); s->g_solve = nullptr; }
+}
+
+void build_graphs(tlpb200_solver* s) {
+    destroy_graphs(s);
+    cudaGraph_t g = nullptr;
+    int64_t cnt = 0;
+    CK(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+    try {
+        enqueue_assemble(s, cnt);
+        enqueue_factor(s, cnt);
+    } catch (...) {
+        cudaStreamEndCapture(s->stream, &g);
+        if (g) cudaGraphDestroy(g);
+        throw;
+    }
+    CK(cudaStreamEndCapture(s->stream, &g));
+    s->launches_update = cnt;
+    CK(cudaGraphInstantiate(&s->g_update, g, 0));
+    CK(cudaGraphDestroy(g));
+    g = nullptr;
+    cnt = 0;
+    CK(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+    try {
+        enqueue_solve(s, s->d_xip, s->d_xid, s->d_dx, s->d_dy, cnt);
+    } catch (...) {
+        cudaStreamEndCapture(s->stream, &g);
+        if (g) cudaGraphDestroy(g);
+        throw;
+    }
+    CK(cudaStreamEndCapture(s->stream, &g));
+    s->launches_solve = cnt;
+    CK(cudaGraphInstantiate(&s->g_solve, g, 0));
+    CK(cudaGraphDestroy(g));
+}
+
+void run_update(tlpb200_solver* s) {
+    if (s->profiling) {
+        int64_t cnt = 0;
+        CK(cudaEventRecord(s->ev[0], s->stream));
+        enqueue_assemble(s, cnt);
+        CK(cudaEventRecord(s->ev[1], s->stream));
+        enqueue_factor(s, cnt);
+        CK(cudaEventRecord(s->ev[2], s->stream));
+        s->launches_update = cnt;
+    } else if (s->opt.use_graph) {
+        if (!s->g_update) build_graphs(s);
+        CK(cudaGraphLaunch(s->g_update, s->stream));
+    } else {
+        int64_t cnt = 0;
+        enqueue_assemble(s, cnt);
+        enqueue_factor(s, cnt);
+        s->launches_update = cnt;
+    }
+    CK(cudaMemcpyAsync(s->h_info, s->ctx.info, sizeof(int32_t), cudaMemcpyDeviceToHost, s->stream));
+    s->n_update++;
+}
+
+int finish_update(tlpb200_solver* s, int64_t* bad_pivot) {
+    CK(cudaStreamSynchronize(s->stream));
+    if (s->profiling) {
+        float a = 0, b = 0;
+        CK(cudaEventElapsedTime(&a, s->ev[0], s->ev[1]));
+        CK(cudaEventElapsedTime(&b, s->ev[1], s->ev[2]));
+        s->ms_assemble = a;
+        s->ms_factor = b;
+    }
+    const int32_t info = *s->h_info;
+    s->bad_pivot = (info >= 0 && info < s->sym.N) ? info : -1;
+    if (bad_pivot) *bad_pivot = s->bad_pivot;
+    if (s->bad_pivot >= 0) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "factorisation breakdown: wrong-sign, zero or NaN pivot at permuted column %lld",
+                 (long long)s->bad_pivot);
+        return fail(s, TLPB200_NOT_POSDEF, buf);
+    }
+    return TLPB200_OK;
+}
+
+// solve one right-hand side held in the internal buffers d_xip/d_xid -> d_dx/d_dy
+void run_solve_internal(tlpb200_solver* s) {
+    if (s->profiling) {
+        int64_t cnt = 0;
+        CK(cudaEventRecord(s->ev[0], s->stream));
+        enqueue_solve(s, s->d_xip, s->d_xid, s->d_dx, s->d_dy, cnt);
+        CK(cudaEventRecord(s->ev[3], s->stream));
+        s->launches_solve = cnt;
+    } else if (s->opt.use_graph) {
+        if (!s->g_solve) build_graphs(s);
+        CK(cudaGraphLaunch(s->g_solve, s->stream));
+    } else {
+        int64_t cnt = 0;
+        enqueue_solve(s, s->d_xip, s->d_xid, s->d_dx, s->d_dy, cnt);
+        s->launches_solve = cnt;
+    }
+    s->n_solve++;
+}
+
+void canonicalize(tlpb200_solver* s, const int64_t* colptr, const int64_t* rowval, const double* nzval, int base) {
+    const int64_t n = s->n, m = s->m;
+    s->colptr.assign(n + 1, 0);
+    std::vector<std::pair<int32_t, double>> col;
+    for (int64_t j = 0; j < n; ++j) {
+        const int64_t b = colptr[j] - base, e = colptr[j + 1] - base;
+        if (b < 0 || e < b) throw std::invalid_argument("colptr is not monotone");
+        col.clear();
+        for (int64_t p = b; p < e; ++p) {
+            const int64_t r = rowval[p] - base;
+            if (r < 0 || r >= m) throw std::invalid_argument("row index out of range");
+            col.emplace_back((int32_t)r, nzval[p]);
+        }
+        std::stable_sort(col.begin(), col.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+        for (size_t x = 0; x < col.size(); ++x) {
+            if (x > 0 && col[x].first == col[x - 1].first) s->val.back() += col[x].second;
+            else { s->rowidx.push_back(col[x].first); s->val.push_back(col[x].second); }
+        }
+        s->colptr[j + 1] = (int64_t)s->rowidx.size();
+    }
+    s->nnz = s->colptr[n];
+}
+
+void setup_device(tlpb200_solver* s) {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) throw CudaFail{e == cudaSuccess ? cudaErrorNoDevice : e, "cudaGetDeviceCount (no CUDA device: this backend has no CPU fallback)"};
+    if (s->opt.device < 0 || s->opt.device >= ndev) throw std::invalid_argument("device ordinal out of range");
+    CK(cudaSetDevice(s->opt.device));
+    s->device = s->opt.device;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, s->device));
+    if (prop.major != 10) throw std::runtime_error("tlpb200 is built for sm_100a (B200) only; found compute capability " + std::to_string(prop.major) + "." + std::to_string(prop.minor));
+    CK(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
+    s->stream = s->own_stream;
+    kernels_static_init();
+    for (auto& ev : s->ev) CK(cudaEventCreate(&ev));
+
+    const Symbolic& S = s->sym;
+    const Plan& P = s->plan;
+    DevCtx& c = s->ctx;
+    c.N = S.N;
+    c.sn_first = upload(s, S.sn_first);
+    c.sn_rowptr = upload(s, S.sn_rowptr);
+    c.sn_rows = upload(s, S.sn_rows);
+    c.sn_xptr = upload(s, S.sn_xptr);
+    c.col2sn = upload(s, S.col2sn);
+    c.sign = upload(s, S.sign);
+    c.diagpos = upload(s, S.diagpos);
+    c.perm = upload(s, S.perm);
+    c.iperm = upload(s, S.iperm);
+    c.pieces = upload(s, P.pieces);
+    c.seg_ptr = upload(s, P.seg_ptr);
+    c.seg_k0 = upload(s, P.seg_k0);
+    c.seg_tgt = upload(s, P.seg_tgt);
+    c.small_list = upload(s, P.small_list);
+    c.level_pieces = upload(s, P.level_pieces);
+    c.upd = upload(s, P.upd);
+    c.panel = upload(s, P.panel);
+    c.solve = upload(s, P.solve);
+    c.Lx = dalloc<double>(s, (size_t)S.lx_size);
+    c.info = dalloc<int32_t>(s, 4);
+    c.wk = dalloc<double>(s, (size_t)S.N);
+    c.acc = dalloc<double>(s, (size_t)S.N);
+    CK(cudaMemset(c.acc, 0, std::max<size_t>(S.N, 1) * sizeof(double)));
+    CK(cudaMemset(c.wk, 0, std::max<size_t>(S.N, 1) * sizeof(double)));
+
+    DevMat& A = s->mat;
+    A.m = s->m; A.n = s->n; A.nnz = s->nnz;
+    A.colptr = upload(s, s->colptr);
+    A.rowidx = upload(s, s->rowidx);
+    A.val = upload(s, s->val);
+    {   // CSR copy for the K1 right-hand side product
+        std::vector<int64_t> rp(s->m + 1, 0);
+        for (int64_t p = 0; p < s->nnz; ++p) rp[s->rowidx[p] + 1]++;
+        for (int64_t i = 0; i < s->m; ++i) rp[i + 1] += rp[i];
+        std::vector<int32_t> ci(s->nnz);
+        std::vector<double> rv(s->nnz);
+        std::vector<int64_t> nxt(rp.begin(), rp.end() - 1);
+        for (int64_t j = 0; j < s->n; ++j)
+            for (int64_t p = s->colptr[j]; p < s->colptr[j + 1]; ++p) {
+                const int64_t q = nxt[s->rowidx[p]]++;
+                ci[q] = (int32_t)j;
+                rv[q] = s->val[p];
+            }
+        A.rowptr = upload(s, rp);
+        A.colidx = upload(s, ci);
+        A.rval = upload(s, rv);
+    }
+    A.nentries = (int64_t)s->maps.w_dest.size();
+    A.w_ptr = upload(s, s->maps.w_ptr);
+    A.w_dest = upload(s, s->maps.w_dest);
+    A.w_col = upload(s, s->maps.w_col);
+    A.w_val = upload(s, s->maps.w_val);
+    A.a_dest = upload(s, s->maps.a_dest);
+
+    s->d_theta = dalloc<double>(s, s->n);
+    s->d_regP = dalloc<double>(s, s->n);
+    s->d_regD = dalloc<double>(s, s->m);
+    s->d_d = dalloc<double>(s, s->n);
+    s->d_xip = dalloc<double>(s, s->m);
+    s->d_xid = dalloc<double>(s, s->n);
+    s->d_dx = dalloc<double>(s, s->n);
+    s->d_dy = dalloc<double>(s, s->m);
+    CK(cudaMallocHost((void**)&s->h_pin, std::max<size_t>(2 * (size_t)(s->n + s->m) + (size_t)s->n, 1) * sizeof(double)));
+    CK(cudaMallocHost((void**)&s->h_info, 4 * sizeof(int32_t)));
+    s->small_smem = small_factor_smem(P.max_small_elems, P.max_small_nrow);
+    s->on_device = true;
+}
+
+}  // namespace
+
+extern "C" {
+
+void tlpb200_default_options(tlpb200_options* o) {
+    std::memset(o, 0, sizeof *o);
+    o->ordering = 1;
+    o->device = 0;
+    o->piece_width = 128;
+    o->small_elems = 4096;
+    o->relax_always = 8;
+    o->use_graph = 1;
+    o->analyze_only = 0;
+}
+
+int tlpb200_create(tlpb200_solver** out, int64_t m, int64_t n, const int64_t* colptr, const int64_t* rowval,
+                   const double* nzval, int index_base, int system, const tlpb200_options* opt) {
+    if (!out) return TLPB200_BAD_ARG;
+    *out = nullptr;
+    tlpb200_solver* s = new (std::nothrow) tlpb200_solver();
+    if (!s) return TLPB200_OOM;
+    *out = s;   // returned even on failure so that tlpb200_last_error() can be read; caller destroys
+    if (opt) s->opt = *opt; else tlpb200_default_options(&s->opt);
+    if (m < 0 || n < 0 || !colptr || (system != TLPB200_K1 && system != TLPB200_K2) || (index_base != 0 && index_base != 1))
+        return fail(s, TLPB200_BAD_ARG, "tlpb200_create: bad argument");
+    if ((system == TLPB200_K1 ? m : m + n) > (int64_t)INT32_MAX - 1)
+        return fail(s, TLPB200_BAD_ARG, "tlpb200_create: system order exceeds 32-bit indexing");
+    if (s->opt.piece_width < 64 || s->opt.piece_width > 128) s->opt.piece_width = 128;
+    if (s->opt.small_elems < 64) s->opt.small_elems = 4096;
+    if (s->opt.small_elems > 8192) s->opt.small_elems = 8192;
+    s->system = system;
+    s->m = m;
+    s->n = n;
+    try {
+        canonicalize(s, colptr, rowval, nzval, index_base);
+        SymOptions so;
+        so.ordering = s->opt.ordering;
+        if (s->opt.relax_always > 0) so.relax_always = s->opt.relax_always;
+        s->sym.system = system;
+        s->sym.m = m;
+        s->sym.n = n;
+        if (system == TLPB200_K1) {
+            SymPattern P = pattern_k1(m, n, s->colptr.data(), s->rowidx.data());
+            analyze_pattern(P, so, nullptr, s->sym);
+        } else {
+            SymPattern P = pattern_k2(m, n, s->colptr.data(), s->rowidx.data());
+            std::vector<int8_t> sg(n + m, 1);
+            for (int64_t j = 0; j < n; ++j) sg[j] = -1;   // first n pivots < 0, last m > 0 (systems.jl:10-32)
+            analyze_pattern(P, so, sg.data(), s->sym);
+        }
+        PlanOptions po;
+        po.piece_width = s->opt.piece_width;
+        po.small_elems = s->opt.small_elems;
+        build_plan(s->sym, po, s->plan);
+        if (system == TLPB200_K1)
+            build_assembly_k1(s->sym, m, n, s->colptr.data(), s->rowidx.data(), s->val.data(), s->maps);
+        else
+            build_assembly_k2(s->sym, m, n, s->colptr.data(), s->rowidx.data(), s->maps);
+        if (!s->opt.analyze_only) setup_device(s);
+    } catch (const CudaFail& f) {
+        return cuda_fail(s, f);
+    } catch (const std::bad_alloc&) {
+        return fail(s, TLPB200_OOM, "host allocation failed during setup");
+    } catch (const std::invalid_argument& e) {
+        return fail(s, TLPB200_BAD_ARG, e.what());
+    } catch (const std::exception& e) {
+        return fail(s, TLPB200_INTERNAL, e.what());
+    }
+    return TLPB200_OK;
+}
+
+#define REQUIRE_DEVICE(s)                                                                              \
+    if (!(s)) return TLPB200_BAD_ARG;                                                                  \
+    if (!(s)->on_device) return fail((s), TLPB200_CUDA, "solver has no device state (analyze_only or failed setup); there is no CPU fallback")
+
+int tlpb200_update(tlpb200_solver* s, const double* theta_inv, const double* regP, const double* regD,
+                   int64_t* bad_pivot) {
+    REQUIRE_DEVICE(s);
+    if (!theta_inv || !regP || !regD) return fail(s, TLPB200_BAD_ARG, "tlpb200_update: null vector");
+    try {
+        CK(cudaSetDevice(s->device));
+        const size_t n = (size_t)s->n, m = (size_t)s->m;
+        std::memcpy(s->h_pin, theta_inv, n * 8);
+        std::memcpy(s->h_pin + n, regP, n * 8);
+        std::memcpy(s->h_pin + 2 * n, regD, m * 8);
+        CK(cudaMemcpyAsync(s->d_theta, s->h_pin, n * 8, cudaMemcpyHostToDevice, s->stream));
+        CK(cudaMemcpyAsync(s->d_regP, s->h_pin + n, n * 8, cudaMemcpyHostToDevice, s->stream));
+        CK(cudaMemcpyAsync(s->d_regD, s->h_pin + 2 * n, m * 8, cudaMemcpyHostToDevice, s->stream));
+        run_update(s);
+        return finish_update(s, bad_pivot);
+    } catch (const CudaFail& f) {
+        return cuda_fail(s, f);
+    }
+}
+
+int tlpb200_update_dev(tlpb200_solver* s, const double* d_theta_inv, const double* d_regP, const double* d_regD) {
+    REQUIRE_DEVICE(s);
+    try {
+        CK(cudaSetDevice(s->device));
+        CK(cudaMemcpyAsync(s->d_theta, d_theta_inv, (size_t)s->n * 8, cudaMemcpyDeviceToDevice, s->stream));
+        CK(cudaMemcpyAsync(s->d_regP, d_regP, (size_t)s->n * 8, cudaMemcpyDeviceToDevice, s->stream));
+        CK(cudaMemcpyAsync(s->d_regD, d_regD, (size_t)s->m * 8, cudaMemcpyDeviceToDevice, s->stream));
+        run_update(s);
+        return TLPB200_OK;
+    } catch (const CudaFail& f) {
+        return cuda_fail(s, f);
+    }
+}
+
+int tlpb200_update_status(tlpb200_solver* s, int64_t* bad_pivot) {
+    REQUIRE_DEVICE(s);
+    try {
+        return finish_update(s, bad_pivot);
+    } catch (const CudaFail& f) {
+        return cuda_fail(s, f);
+    }
+}
+
+int tlpb200_solve(tlpb200_solver* s, double* dx, double* dy, const double* xi_p, const double* xi_d, int32_t nrhs,
+                  int64_t ldx, int64_t ldy) {
+    REQUIRE_DEVICE(s);
+    if (!dx || !dy || !xi_p || !xi_d || nrhs < 1 || (nrhs > 1 && (ldx < s->n || ldy < s->m)))
+        return fail(s, TLPB200_BAD_ARG, "tlpb200_solve: bad argument");
+    try {
+        CK(cudaSetDevice(s->device));
+        const size_t n = (size_t)s->n, m = (size_t)s->m;
+        double* hin = s->h_pin;
+        double* hout = s->h_pin + (n + m);
+        for (int32_t r = 0; r < nrhs; ++r) {
+            std::memcpy(hin, xi_p + (size_t)r * ldy, m * 8);
+            std::memcpy(hin + m, xi_d + (size_t)r * ldx, n * 8);
+            CK(cudaMemcpyAsync(s->d_xip, hin, m * 8, cudaMemcpyHostToDevice, s->stream));
+            CK(cudaMemcpyAsync(s->d_xid, hin + m, n * 8, cudaMemcpyHostToDevice, s->stream));
+            run_solve_internal(s);
+            CK(cudaMemcpyAsync(hout, s->d_dx, n * 8, cudaMemcpyDeviceToHost, s->stream));
+            CK(cudaMemcpyAsync(hout + n, s->d_dy, m * 8, cudaMemcpyDeviceToHost, s->stream));
+            CK(cudaStreamSynchronize(s->stream));
+            if (s->profiling) {
+                float a = 0;
+                CK(cudaEventElapsedTime(&a, s->ev[0], s->ev[3]));
+                s->ms_solve = a;
+            }
+            std::memcpy(dx + (size_t)r * ldx, hout, n * 8);
+            std::memcpy(dy + (size_t)r * ldy, hout + n, m * 8);
+        }
+        return TLPB200_OK;
+    } catch (const CudaFail& f) {
+        return cuda_fail(s, f);
+    }
+}
+
+int tlpb200_solve_dev(tlpb200_solver* s, double* d_dx, double* d_dy, const double* d_xi_p, const double* d_xi_d,
+                      int32_t nrhs, int64_t ldx, int64_t ldy) {
+    REQUIRE_DEVICE(s);
+    if (nrhs < 1) return fail(s, TLPB200_BAD_ARG, "tlpb200_solve_dev: nrhs < 1");
+    try {
+        CK(cudaSetDevice(s->device));
+        const size_t n = (size_t)s->n, m = (size_t)s->m;
+        for (int32_t r = 0; r < nrhs; ++r) {
+            CK(cudaMemcpyAsync(s->d_xip, d_xi_p + (size_t)r * ldy, m * 8, cudaMemcpyDeviceToDevice, s->stream));
+            CK(cudaMemcpyAsync(s->d_xid, d_xi_d + (size_t)r * ldx, n * 8, cudaMemcpyDeviceToDevice, s->stream));
+            run_solve_internal(s);
+            CK(cudaMemcpyAsync(d_dx + (size_t)r * ldx, s->d_dx, n * 8, cudaMemcpyDeviceToDevice, s->stream));
+            CK(cudaMemcpyAsync(d_dy + (size_t)r * ldy, s->d_dy, m * 8, cudaMemcpyDeviceToDevice, s->stream));
+        }
+        return TLPB200_OK;
+    } catch (const CudaFail& f) {
+        return cuda_fail(s, f);
+    }
+}
+
+int tlpb200_set_stream(tlpb200_solver* s, void* cuda_stream) {
+    REQUIRE_DEVICE(s);
+    cudaStreamSynchronize(s->stream);
+    s->stream = cuda_stream ? (cudaStream_t)cuda_stream : s->own_stream;
+    destroy_graphs(s);   // graphs are captured per stream
+    return TLPB200_OK;
+}
+
+int tlpb200_synchronize(tlpb200_solver* s) {
+    REQUIRE_DEVICE(s);
+    cudaError_t e = cudaStreamSynchronize(s->stream);
+    if (e != cudaSuccess) return cuda_fail(s, CudaFail{e, "cudaStreamSynchronize"});
+    return TLPB200_OK;
+}
+
+int tlpb200_set_profiling(tlpb200_solver* s, int on) {
+    REQUIRE_DEVICE(s);
+    s->profiling = on != 0;
+    return TLPB200_OK;
+}
+
+int tlpb200_stats_get(const tlpb200_solver* s, tlpb200_stats* o) {
+    if (!s || !o) return TLPB200_BAD_ARG;
+    std::memset(o, 0, sizeof *o);
+    o->m = s->m; o->n = s->n; o->nnzA = s->nnz;
+    o->order = s->sym.N;
+    o->nnzL = s->sym.nnzL;
+    o->nnzL_stored = s->sym.lx_size;
+    o->flops = s->sym.flops;
+    o->nsuper = s->sym.nsuper;
+    o->npieces = (int64_t)s->plan.pieces.size();
+    o->nlevels = (int64_t)s->plan.levels.size();
+    o->max_ncol = s->sym.max_ncol;
+    o->max_nrow = s->sym.max_nrow;
+    o->nproducts = (int64_t)s->maps.w_col.size();
+    o->nentries = (int64_t)s->maps.w_dest.size();
+    o->launches_update = s->launches_update;
+    o->launches_solve = s->launches_solve;
+    o->ms_assemble = s->ms_assemble;
+    o->ms_factor = s->ms_factor;
+    o->ms_solve = s->ms_solve;
+    o->bad_pivot = s->bad_pivot;
+    o->n_update = s->n_update;
+    o->n_solve = s->n_solve;
+    o->bytes_device = (int64_t)s->bytes_device;
+    return TLPB200_OK;
+}
+
+int tlpb200_get_symbolic(const tlpb200_solver* s, int32_t* perm, int32_t* parent, int32_t* colcount, int32_t* sn_first) {
+    if (!s) return TLPB200_BAD_ARG;
+    const Symbolic& S = s->sym;
+    if (perm) std::copy(S.perm.begin(), S.perm.end(), perm);
+    if (parent) std::copy(S.parent.begin(), S.parent.end(), parent);
+    if (colcount) std::copy(S.colcount.begin(), S.colcount.end(), colcount);
+    if (sn_first) std::copy(S.sn_first.begin(), S.sn_first.end(), sn_first);
+    return TLPB200_OK;
+}
+
+int tlpb200_get_structure(const tlpb200_solver* s, int64_t* rowptr, int32_t* rows) {
+    if (!s) return TLPB200_BAD_ARG;
+    const Symbolic& S = s->sym;
+    if (rowptr) std::copy(S.sn_rowptr.begin(), S.sn_rowptr.end(), rowptr);
+    if (rows) std::copy(S.sn_rows.begin(), S.sn_rows.end(), rows);
+    return TLPB200_OK;
+}
+
+int tlpb200_debug_assemble(tlpb200_solver* s, const double* theta_inv, const double* regP, const double* regD) {
+    REQUIRE_DEVICE(s);
+    try {
+        CK(cudaSetDevice(s->device));
+        CK(cudaMemcpyAsync(s->d_theta, theta_inv, (size_t)s->n * 8, cudaMemcpyHostToDevice, s->stream));
+        CK(cudaMemcpyAsync(s->d_regP, regP, (size_t)s->n * 8, cudaMemcpyHostToDevice, s->stream));
+        CK(cudaMemcpyAsync(s->d_regD, regD, (size_t)s->m * 8, cudaMemcpyHostToDevice, s->stream));
+        int64_t cnt = 0;
+        enqueue_assemble(s, cnt);
+        CK(cudaStreamSynchronize(s->stream));
+        return TLPB200_OK;
+    } catch (const CudaFail& f) {
+        return cuda_fail(s, f);
+    }
+}
+
+int tlpb200_debug_get_lx(tlpb200_solver* s, double* lx, int64_t* xptr) {
+    REQUIRE_DEVICE(s);
+    try {
+        CK(cudaSetDevice(s->device));
+        CK(cudaStreamSynchronize(s->stream));
+        if (lx) CK(cudaMemcpy(lx, s->ctx.Lx, (size_t)s->sym.lx_size * 8, cudaMemcpyDeviceToHost));
+        if (xptr) std::copy(s->sym.sn_xptr.begin(), s->sym.sn_xptr.end(), xptr);
+        return TLPB200_OK;
+    } catch (const CudaFail& f) {
+        return cuda_fail(s, f);
+    }
+}
+
+const char* tlpb200_last_error(const tlpb200_solver* s) { return s ? s->err.c_str() : "null solver"; }
+const char* tlpb200_backend_name(void) { return "TlpB200 (supernodal signed Cholesky, CUDA sm_100a)"; }
+const char* tlpb200_linear_system(const tlpb200_solver* s) {
+    if (!s) return "Unknown";
+    return s->system == TLPB200_K1 ? "Normal equations (K1)" : "Augmented system (K2)";
+}
+
+void tlpb200_destroy(tlpb200_solver* s) {
+    if (!s) return;
+    if (s->on_device) {
+        cudaSetDevice(s->device);
+        cudaStreamSynchronize(s->stream);
+        destroy_graphs(s);
+        for (void* p : s->allocs) cudaFree(p);
+        if (s->h_pin) cudaFreeHost(s->h_pin);
+        if (s->h_info) cudaFreeHost(s->h_info);
+        for (auto& ev : s->ev) if (ev) cudaEventDestroy(ev);
+        if (s->own_stream) cudaStreamDestroy(s->own_stream);
+    }
+    delete s;
+}
+
+}  // extern "C"
