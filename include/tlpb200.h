@@ -67,6 +67,14 @@ typedef struct tlpb200_stats {
     int64_t bad_pivot;      /* permuted column of the first bad pivot of the last update!, -1 if none */
     int64_t n_update, n_solve;
     int64_t bytes_device;
+    /* algorithmic flops (2 per multiply-add, lower triangle only) of the tile-update kernel launches of
+     * one update!: inside column pieces (incl. the fused 64x64 potrf) / to the rest of the matrix */
+    double flops_update_inner, flops_update_ext;
+    /* profiling mode: CUDA-event time and launch count per kernel class of the last update!/solve!
+     * 0 assemble  1 small_factor  2 update_inner  3 trsm  4 update_ext  5 rhs+recover
+     * 6 fwd_small 7 fwd_trsv 8 fwd_gemv 9 bwd_gemv 10 bwd_trsv 11 bwd_small */
+    double ms_class[16];
+    int64_t n_class[16];
 } tlpb200_stats;
 
 void tlpb200_default_options(tlpb200_options* opt);

@@ -1,0 +1,265 @@
+"""GPU parity tests (run on the B200 box with ``-m gpu``): the CUDA path, called through the C ABI,
+against the oracle on the same seeded inputs; bit-level structure checks; reference error
+behaviour; end-to-end IPM parity; size-independent properties at BASELINE sizes.
+
+Tolerances: BASELINE.json north_star asks 1e-8 relative on objectives/residuals; the reference's
+own KKT test asks residuals <= sqrt(eps) (src/KKT/Test/test.jl:39-44)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import tlpb200_loader
+from golden.lpex import KKT_CONFORMANCE, LPEX
+from oracle import hsd_ref, kkt_ref
+
+pkg = tlpb200_loader.load()
+from tulip_jl_b200 import hsd, lpgen  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+SQRT_EPS = float(np.sqrt(np.finfo(float).eps))
+SYSTEMS = {"K1": pkg.K1, "K2": pkg.K2}
+
+
+def _oracle(A, sysname):
+    return kkt_ref.SparseK1(A) if sysname == "K1" else kkt_ref.SparseK2(A)
+
+
+def _dense_from_lx(k, lx, xptr):
+    """Rebuild the dense lower-triangular array stored in the supernodal panels."""
+    sym = k.symbolic()
+    N = len(sym["perm"])
+    L = np.zeros((N, N))
+    first, rp, rows = sym["sn_first"], sym["sn_rowptr"], sym["sn_rows"]
+    for s in range(len(first) - 1):
+        f, l = first[s], first[s + 1]
+        r = rows[rp[s]:rp[s + 1]]
+        P = lx[xptr[s]:xptr[s + 1]].reshape(l - f, len(r)).T      # column-major nrow x ncol
+        for c in range(l - f):
+            L[r[c:], f + c] = P[c:, c]
+    return L, sym
+
+
+def _kkt_matrix(A, sysname, theta, regP, regD):
+    A = sp.csc_matrix(A)
+    if sysname == "K1":
+        return (A @ sp.diags(1.0 / (theta + regP)) @ A.T + sp.diags(regD)).toarray()
+    return sp.bmat([[sp.diags(-(theta + regP)), A.T], [A, sp.diags(regD)]]).toarray()
+
+
+@pytest.mark.parametrize("sysname", ["K1", "K2"])
+def test_reference_conformance(sysname):
+    """test/KKT/Cholmod/cholmod.jl:8-16 with the new backend: KKT.run_ls_tests(A, kkt)."""
+    A = KKT_CONFORMANCE["A"]
+    kkt = pkg.setup(sp.csc_matrix(A), SYSTEMS[sysname](), pkg.Backend())
+    rp, rd, dx, dy = kkt_ref.run_ls_tests(A, kkt)
+    assert rp <= SQRT_EPS and rd <= SQRT_EPS
+    np.testing.assert_allclose(dx, KKT_CONFORMANCE["dx"], atol=1e-14)
+    np.testing.assert_allclose(dy, KKT_CONFORMANCE["dy"], atol=1e-14)
+
+
+@pytest.mark.parametrize("cfg", [2, 3, 4, 5, "T"])
+@pytest.mark.parametrize("sysname", ["K1", "K2"])
+def test_assemble_and_factor_parity(cfg, sysname):
+    """assemble kernel == A D A' + Rd (spd.jl:43) / K2 matrix (sqd.jl:44-51) to 1e-14;
+    numeric factor: |L S L' - P K P'| <= 1e-12 |L||L'| componentwise (backward-error bound)."""
+    lp = lpgen.config(cfg, mini=True)
+    m, n = lp.A.shape
+    rng = np.random.default_rng(11)
+    theta = np.exp(rng.uniform(-5, 5, n)); regP = np.full(n, 1e-7); regD = np.full(m, 1e-7)
+    k = pkg.setup(lp.A, SYSTEMS[sysname](), pkg.Backend())
+    K = _kkt_matrix(lp.A, sysname, theta, regP, regD)
+    lx, xptr = k.debug_assembled(theta, regP, regD)
+    Lasm, sym = _dense_from_lx(k, lx, xptr)
+    p = sym["perm"]
+    Kp = K[np.ix_(p, p)]
+    np.testing.assert_allclose(Lasm, np.tril(Kp), rtol=1e-13, atol=1e-14 * np.abs(K).max())
+    k.update(theta, regP, regD)
+    lx, xptr = k.debug_lx()
+    L, _ = _dense_from_lx(k, lx, xptr)
+    sgn = np.ones(len(p)) if sysname == "K1" else np.where(p < n, -1.0, 1.0)
+    R = (L * sgn[None, :]) @ L.T
+    # componentwise backward-error bound of a Cholesky/LDL' without pivoting: |K - L S L'| <= c*N*u*|L||L'|
+    bound = 1e-12 * (np.abs(L) @ np.abs(L).T) + 1e-300
+    assert np.all(np.abs(R - Kp) <= bound), float((np.abs(R - Kp) / bound).max())
+
+
+@pytest.mark.parametrize("cfg", [2, 3, 4, 5, "T"])
+@pytest.mark.parametrize("sysname", ["K1", "K2"])
+def test_solve_parity_vs_oracle(cfg, sysname):
+    """per-call parity (SURVEY 8d protocol i): same (θ, regP, regD, ξp, ξd) -> same (dx, dy)."""
+    lp = lpgen.config(cfg, mini=True)
+    A = lp.A
+    m, n = A.shape
+    rng = np.random.default_rng(3)
+    k = pkg.setup(A, SYSTEMS[sysname](), pkg.Backend())
+    o = _oracle(A, sysname)
+    for spread, reg in ((3.0, 1e-4), (8.0, 1e-6)):
+        theta = np.exp(rng.uniform(-spread, spread, n))
+        theta[rng.random(n) < 0.05] = 0.0                       # free variables: θinv_j = 0
+        regP = np.full(n, reg); regD = np.full(m, reg)
+        xi_p = rng.standard_normal(m); xi_d = rng.standard_normal(n)
+        k.update(theta, regP, regD)
+        o.update(theta, regP, regD)
+        dx = np.zeros(n); dy = np.zeros(m); dx0 = np.zeros(n); dy0 = np.zeros(m)
+        k.solve(dx, dy, xi_p, xi_d)
+        o.solve(dx0, dy0, xi_p, xi_d)
+        rp, rd = kkt_ref.kkt_residuals(A, theta, regP, regD, dx, dy, xi_p, xi_d)
+        rp0, rd0 = kkt_ref.kkt_residuals(A, theta, regP, regD, dx0, dy0, xi_p, xi_d)
+        scale = max(1.0, np.abs(dx0).max(), np.abs(dy0).max())
+        # device residuals no worse than 10x the oracle's (both are backward-stable factorizations)
+        assert rp <= max(10 * rp0, SQRT_EPS * scale) and rd <= max(10 * rd0, SQRT_EPS * scale)
+        ex = np.abs(dx - dx0).max() / max(np.abs(dx0).max(), 1e-300)
+        ey = np.abs(dy - dy0).max() / max(np.abs(dy0).max(), 1e-300)
+        assert ex <= 1e-8 and ey <= 1e-8, (ex, ey)
+
+
+def test_errors_match_reference():
+    A = lpgen.config(2, mini=True).A
+    m, n = A.shape
+    for sysname in ("K1", "K2"):
+        k = pkg.setup(A, SYSTEMS[sysname](), pkg.Backend())
+        with pytest.raises(pkg.DimensionMismatch):                 # spd.jl:26-34
+            k.update(np.ones(n - 1), np.ones(n), np.ones(m))
+        with pytest.raises(pkg.DimensionMismatch):
+            k.update(np.ones(n), np.ones(n), np.ones(m + 2))
+        with pytest.raises(pkg.PosDefException):                   # spd.jl:47 / ldlfact.jl:112-117
+            k.update(np.ones(n), np.ones(n), -1e3 * np.ones(m))
+        with pytest.raises(pkg.PosDefException):
+            k.update(np.full(n, np.nan), np.ones(n), np.ones(m))
+        # the solver stays usable after a failed update (regularisation bump path, step.jl:34-51)
+        k.update(np.ones(n), np.ones(n), np.ones(m))
+        dx = np.zeros(n); dy = np.zeros(m)
+        k.solve(dx, dy, np.ones(m), np.ones(n))
+        rp, rd = kkt_ref.kkt_residuals(A, np.ones(n), np.ones(n), np.ones(m), dx, dy, np.ones(m), np.ones(n))
+        assert rp <= SQRT_EPS and rd <= SQRT_EPS
+    k2 = pkg.setup(A, pkg.K2(), pkg.Backend())
+    with pytest.raises(pkg.PosDefException):                       # wrong sign in the (1,1) block
+        k2.update(-5 * np.ones(n), np.ones(n), np.ones(m))
+
+
+@pytest.mark.parametrize("name", list(LPEX))
+@pytest.mark.parametrize("sysname", ["K1", "K2"])
+def test_example_lps_end_to_end(name, sysname):
+    """test/examples.jl with KKT_Backend = TlpB200: statuses and values the reference asserts."""
+    lp = LPEX[name]
+    dat = hsd_ref.standard_form(**{k: v for k, v in lp.items() if k != "expect"})
+    kkt = pkg.setup(dat.A, SYSTEMS[sysname](), pkg.Backend())
+    h = hsd.HSD(dat.A, dat.b, dat.c, dat.l, dat.u, kkt, c0=dat.c0, objsense=dat.objsense)
+    status = h.optimize()
+    exp = lp["expect"]
+    tol = 100 * SQRT_EPS
+    assert status == exp["status"]
+    if "obj" in exp:
+        assert abs(h.primal_objective - exp["obj"]) <= tol * (1 + abs(exp["obj"]))
+    if "x" in exp:
+        np.testing.assert_allclose(h.x[:lp["nvar"]] / h.tau, exp["x"], atol=tol, rtol=tol)
+    if "y" in exp:
+        np.testing.assert_allclose(h.y / h.tau, exp["y"], atol=tol, rtol=tol)
+
+
+@pytest.mark.parametrize("cfg,sysname", [(2, "K1"), (3, "K2"), (4, "K1"), (5, "K2"), ("T", "K1")])
+def test_ipm_end_to_end_parity(cfg, sysname):
+    """SURVEY 8d protocol ii: the restated HSD run with the oracle KKT and with the device KKT,
+    tolerances tightened to 1e-10, objectives and residual norms agree to 1e-8 relative."""
+    lp = lpgen.config(cfg, mini=True)
+    P = dict(TolerancePFeas=1e-10, ToleranceDFeas=1e-10, ToleranceRGap=1e-10)
+    dat = hsd_ref.IPMData(lp.A, lp.b, True, lp.c, 0.0, lp.l, lp.u)
+    ref = hsd_ref.HSDRef(dat, _oracle(lp.A, sysname), hsd_ref.IPMOptions(**P))
+    ref.optimize()
+    kkt = pkg.setup(lp.A, SYSTEMS[sysname](), pkg.Backend())
+    h = hsd.HSD(lp.A, lp.b, lp.c, lp.l, lp.u, kkt, params=hsd.IPMOptions(**P))
+    h.optimize()
+    assert h.status == ref.status == "Trm_Optimal"
+    assert abs(h.niter - ref.niter) <= 1
+    for a, b in ((h.primal_objective, ref.primal_objective), (h.dual_objective, ref.dual_objective)):
+        assert abs(a - b) <= 1e-8 * (1 + abs(b))
+    assert h.rp_nrm <= 1e-8 * (1 + np.abs(lp.b).max()) and h.rd_nrm <= 1e-8 * (1 + np.abs(lp.c).max())
+
+
+def test_multi_rhs_and_device_pointer_api():
+    torch = pytest.importorskip("torch")
+    lp = lpgen.config(2, mini=True)
+    A = lp.A
+    m, n = A.shape
+    rng = np.random.default_rng(9)
+    theta = np.exp(rng.uniform(-4, 4, n)); regP = np.full(n, 1e-6); regD = np.full(m, 1e-6)
+    for sysname in ("K1", "K2"):
+        k = pkg.setup(A, SYSTEMS[sysname](), pkg.Backend())
+        k.update(theta, regP, regD)
+        XP = rng.standard_normal((3, m)); XD = rng.standard_normal((3, n))
+        DX = np.zeros((3, n)); DY = np.zeros((3, m))
+        k.solve_multi(DX, DY, XP, XD)
+        for r in range(3):
+            dx = np.zeros(n); dy = np.zeros(m)
+            k.solve(dx, dy, XP[r], XD[r])
+            assert np.array_equal(dx, DX[r]) and np.array_equal(dy, DY[r])
+        # device-resident inputs on torch's current stream
+        dev = torch.device("cuda:0")
+        k.set_stream(torch.cuda.current_stream().cuda_stream)
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        k.update_dev(t(theta), t(regP), t(regD))
+        k.update_status()
+        ddx = torch.zeros(n, dtype=torch.float64, device=dev); ddy = torch.zeros(m, dtype=torch.float64, device=dev)
+        k.solve_dev(ddx, ddy, t(XP[0]), t(XD[0]))
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(ddx.cpu().numpy(), DX[0], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(ddy.cpu().numpy(), DY[0], rtol=1e-9, atol=1e-12)
+
+
+def test_graph_and_plain_launch_agree():
+    lp = lpgen.config(4, mini=True)
+    A = lp.A
+    m, n = A.shape
+    rng = np.random.default_rng(2)
+    theta = np.exp(rng.uniform(-4, 4, n)); regP = np.full(n, 1e-6); regD = np.full(m, 1e-6)
+    xi_p = rng.standard_normal(m); xi_d = rng.standard_normal(n)
+    out = []
+    for graph in (True, False):
+        k = pkg.setup(A, pkg.K1(), pkg.Backend(use_graph=graph))
+        k.update(theta, regP, regD)
+        dx = np.zeros(n); dy = np.zeros(m)
+        k.solve(dx, dy, xi_p, xi_d)
+        out.append(np.concatenate([dx, dy]))
+        st = k.stats()
+        assert st["launches_update"] > 0 and st["launches_solve"] > 0
+    np.testing.assert_allclose(out[0], out[1], rtol=1e-9, atol=1e-12)
+
+
+def test_empty_and_ragged_inputs():
+    """empty columns, a column of explicit zeros, a single row."""
+    rng = np.random.default_rng(4)
+    A = sp.csc_matrix((np.array([1.0, 2.0, 0.0, -1.0]), (np.array([0, 2, 1, 1]), np.array([1, 3, 4, 5]))), shape=(3, 7))
+    A = (A + sp.eye(3, 7)).tocsc()
+    for sysname in ("K1", "K2"):
+        k = pkg.setup(A, SYSTEMS[sysname](), pkg.Backend())
+        m, n = A.shape
+        th = np.exp(rng.uniform(-2, 2, n)); rP = np.full(n, 1e-3); rD = np.full(m, 1e-3)
+        k.update(th, rP, rD)
+        dx = np.zeros(n); dy = np.zeros(m); xp = rng.standard_normal(m); xd = rng.standard_normal(n)
+        k.solve(dx, dy, xp, xd)
+        rp, rd = kkt_ref.kkt_residuals(A, th, rP, rD, dx, dy, xp, xd)
+        assert rp <= 1e-10 and rd <= 1e-10
+
+
+@pytest.mark.parametrize("cfg,sysname", [(2, "K1"), (3, "K2")])
+def test_full_size_properties(cfg, sysname):
+    """BASELINE sizes: KKT residual (test.jl:39-40 formulas) and linearity of solve! in the rhs."""
+    lp = lpgen.config(cfg)
+    A = lp.A
+    m, n = A.shape
+    rng = np.random.default_rng(8)
+    theta = np.exp(rng.uniform(-3, 3, n)); regP = np.full(n, 1e-6); regD = np.full(m, 1e-6)
+    k = pkg.setup(A, SYSTEMS[sysname](), pkg.Backend())
+    k.update(theta, regP, regD)
+    xs = []
+    rhs = [(rng.standard_normal(m), rng.standard_normal(n)) for _ in range(2)]
+    rhs.append((2.0 * rhs[0][0] - 3.0 * rhs[1][0], 2.0 * rhs[0][1] - 3.0 * rhs[1][1]))
+    for xp, xd in rhs:
+        dx = np.zeros(n); dy = np.zeros(m)
+        k.solve(dx, dy, xp, xd)
+        rp, rd = kkt_ref.kkt_residuals(A, theta, regP, regD, dx, dy, xp, xd)
+        scale = max(1.0, np.abs(dx).max(), np.abs(dy).max())
+        assert rp <= SQRT_EPS * scale and rd <= SQRT_EPS * scale
+        xs.append(np.concatenate([dx, dy]))
+    comb = 2.0 * xs[0] - 3.0 * xs[1]
+    assert np.abs(xs[2] - comb).max() <= 1e-7 * max(1.0, np.abs(comb).max())

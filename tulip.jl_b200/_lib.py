@@ -32,10 +32,20 @@ class Stats(C.Structure):
                 ("launches_update", C.c_int64), ("launches_solve", C.c_int64),
                 ("ms_assemble", C.c_double), ("ms_factor", C.c_double), ("ms_solve", C.c_double),
                 ("bad_pivot", C.c_int64), ("n_update", C.c_int64), ("n_solve", C.c_int64),
-                ("bytes_device", C.c_int64)]
+                ("bytes_device", C.c_int64),
+                ("flops_update_inner", C.c_double), ("flops_update_ext", C.c_double),
+                ("ms_class", C.c_double * 16), ("n_class", C.c_int64 * 16)]
 
     def asdict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_}
+        d = {}
+        for k, _ in self._fields_:
+            v = getattr(self, k)
+            d[k] = list(v) if hasattr(v, "__len__") else v
+        return d
+
+
+KERNEL_CLASSES = ["assemble", "small_factor", "update_inner", "trsm", "update_ext", "rhs_recover",
+                  "fwd_small", "fwd_trsv", "fwd_gemv", "bwd_gemv", "bwd_trsv", "bwd_small"]
 
 
 # every symbol include/tlpb200.h declares (tests check that the library exports all of them)

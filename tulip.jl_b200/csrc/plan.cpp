@@ -200,6 +200,21 @@ void build_plan(const Symbolic& S, const PlanOptions& opt, Plan& P) {
         }
         lp.solve_end = (int32_t)P.solve.size();
     }
+    // algorithmic flops of the tile updates: 2*kdim per structurally needed output entry
+    auto tile_flops = [](const UpdTask& t) {
+        double ent = (double)t.ni * t.nk;
+        if (t.diag) ent -= (double)t.nk * (t.nk - 1) / 2.0;
+        return 2.0 * ent * (double)t.kdim;
+    };
+    P.flops_update_inner = P.flops_update_ext = 0.0;
+    for (const LevelPlan& lp : P.levels) {
+        for (int32_t t = 0; t < lp.nsteps; ++t)
+            for (int32_t x = lp.inner_begin[t]; x < lp.inner_end[t]; ++x) {
+                P.flops_update_inner += tile_flops(P.upd[x]);
+                if (P.upd[x].diag == 2) P.flops_update_inner += (double)P.upd[x].nk * P.upd[x].nk * P.upd[x].nk / 3.0;
+            }
+        for (int32_t x = lp.ext_begin; x < lp.ext_end; ++x) P.flops_update_ext += tile_flops(P.upd[x]);
+    }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -75,6 +75,7 @@ struct Plan {
     std::vector<LevelPlan> levels;
     int32_t max_small_elems = 0;          // largest nrow*ncol among small supernodes
     int32_t max_small_nrow = 0;
+    double flops_update_inner = 0.0, flops_update_ext = 0.0;   // algorithmic (lower-triangle) flops of the tile updates
 };
 
 void build_plan(const Symbolic& S, const PlanOptions& opt, Plan& P);

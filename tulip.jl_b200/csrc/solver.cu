@@ -51,6 +51,13 @@ struct tlpb200_solver {
     bool profiling = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 
+    // per-kernel-class profiling (profiling mode only)
+    std::vector<cudaEvent_t> pool;
+    std::vector<int> pool_cls;
+    size_t pool_used = 0;
+    double ms_class[16] = {0};
+    int64_t n_class[16] = {0};
+
     int64_t launches_update = 0, launches_solve = 0;
     double ms_assemble = 0, ms_factor = 0, ms_solve = 0;
     int64_t bad_pivot = -1, n_update = 0, n_solve = 0;
@@ -92,6 +99,40 @@ int fail(tlpb200_solver* s, int code, const std::string& msg) {
     return code;
 }
 
+// RAII event bracket around one launch (only active in profiling mode)
+struct Scope {
+    tlpb200_solver* s;
+    bool on;
+    Scope(tlpb200_solver* s_, int cls) : s(s_), on(s_->profiling) {
+        if (!on) return;
+        if (s->pool_used + 2 > s->pool.size()) {
+            for (int k = 0; k < 2; ++k) { cudaEvent_t e; cudaEventCreate(&e); s->pool.push_back(e); }
+        }
+        s->pool_cls.resize(s->pool.size() / 2);
+        s->pool_cls[s->pool_used / 2] = cls;
+        cudaEventRecord(s->pool[s->pool_used], s->stream);
+    }
+    ~Scope() {
+        if (!on) return;
+        cudaEventRecord(s->pool[s->pool_used + 1], s->stream);
+        s->pool_used += 2;
+    }
+};
+
+void collect_profile(tlpb200_solver* s, bool reset_update_classes) {
+    // called after a stream sync
+    const int lo = reset_update_classes ? 0 : 5, hi = reset_update_classes ? 5 : 12;
+    for (int c = lo; c < hi; ++c) { s->ms_class[c] = 0; s->n_class[c] = 0; }
+    for (size_t i = 0; i + 1 < s->pool_used; i += 2) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, s->pool[i], s->pool[i + 1]);
+        const int c = s->pool_cls[i / 2];
+        s->ms_class[c] += ms;
+        s->n_class[c] += 1;
+    }
+    s->pool_used = 0;
+}
+
 int cuda_fail(tlpb200_solver* s, const CudaFail& f) {
     char buf[512];
     snprintf(buf, sizeof buf, "CUDA error %d (%s) in %s", (int)f.e, cudaGetErrorString(f.e), f.what);
@@ -102,6 +143,7 @@ int cuda_fail(tlpb200_solver* s, const CudaFail& f) {
 // ---- the numeric phases, enqueued on s->stream; `count` accumulates kernel launches -------------
 void enqueue_assemble(tlpb200_solver* s, int64_t& count) {
     cudaStream_t st = s->stream;
+    Scope sc(s, 0);
     CK(cudaMemsetAsync(s->ctx.Lx, 0, (size_t)s->sym.lx_size * sizeof(double), st));
     CK(cudaMemsetAsync(s->ctx.info, 0x7f, sizeof(int32_t), st));
     if (s->system == TLPB200_K1) {
@@ -118,38 +160,45 @@ void enqueue_factor(tlpb200_solver* s, int64_t& count) {
     cudaStream_t st = s->stream;
     for (const LevelPlan& lp : s->plan.levels) {
         if (lp.small_end > lp.small_begin) {
+            Scope sc(s, 1);
             launch_small_factor(s->ctx, lp.small_begin, lp.small_end, s->small_smem, st);
             count++;
         }
         for (int t = 0; t < lp.nsteps; ++t) {
-            if (lp.inner_end[t] > lp.inner_begin[t]) { launch_update(s->ctx, lp.inner_begin[t], lp.inner_end[t], 0, st); count++; }
-            if (lp.panel_end[t] > lp.panel_begin[t]) { launch_trsm(s->ctx, lp.panel_begin[t], lp.panel_end[t], st); count++; }
+            if (lp.inner_end[t] > lp.inner_begin[t]) { Scope sc(s, 2); launch_update(s->ctx, lp.inner_begin[t], lp.inner_end[t], 0, st); count++; }
+            if (lp.panel_end[t] > lp.panel_begin[t]) { Scope sc(s, 3); launch_trsm(s->ctx, lp.panel_begin[t], lp.panel_end[t], st); count++; }
         }
-        if (lp.ext_end > lp.ext_begin) { launch_update(s->ctx, lp.ext_begin, lp.ext_end, lp.ext_atomic, st); count++; }
+        if (lp.ext_end > lp.ext_begin) { Scope sc(s, 4); launch_update(s->ctx, lp.ext_begin, lp.ext_end, lp.ext_atomic, st); count++; }
     }
     CK(cudaGetLastError());
 }
 
 void enqueue_solve(tlpb200_solver* s, const double* xip, const double* xid, double* dx, double* dy, int64_t& count) {
     cudaStream_t st = s->stream;
-    if (s->system == TLPB200_K1) launch_k1_rhs(s->ctx, s->mat, s->d_d, xip, xid, st);
-    else launch_k2_rhs(s->ctx, s->mat, xip, xid, st);
+    {
+        Scope sc(s, 5);
+        if (s->system == TLPB200_K1) launch_k1_rhs(s->ctx, s->mat, s->d_d, xip, xid, st);
+        else launch_k2_rhs(s->ctx, s->mat, xip, xid, st);
+    }
     count++;
     const auto& L = s->plan.levels;
     for (size_t l = 0; l < L.size(); ++l) {
         const LevelPlan& lp = L[l];
-        if (lp.small_end > lp.small_begin) { launch_fwd_small(s->ctx, lp.small_begin, lp.small_end, st); count++; }
-        if (lp.piece_end > lp.piece_begin) { launch_fwd_trsv(s->ctx, lp.piece_begin, lp.piece_end, st); count++; }
-        if (lp.solve_end > lp.solve_begin) { launch_fwd_gemv(s->ctx, lp.solve_begin, lp.solve_end, st); count++; }
+        if (lp.small_end > lp.small_begin) { Scope sc(s, 6); launch_fwd_small(s->ctx, lp.small_begin, lp.small_end, st); count++; }
+        if (lp.piece_end > lp.piece_begin) { Scope sc(s, 7); launch_fwd_trsv(s->ctx, lp.piece_begin, lp.piece_end, st); count++; }
+        if (lp.solve_end > lp.solve_begin) { Scope sc(s, 8); launch_fwd_gemv(s->ctx, lp.solve_begin, lp.solve_end, st); count++; }
     }
     for (size_t l = L.size(); l-- > 0;) {
         const LevelPlan& lp = L[l];
-        if (lp.solve_end > lp.solve_begin) { launch_bwd_gemv(s->ctx, lp.solve_begin, lp.solve_end, st); count++; }
-        if (lp.piece_end > lp.piece_begin) { launch_bwd_trsv(s->ctx, lp.piece_begin, lp.piece_end, st); count++; }
-        if (lp.small_end > lp.small_begin) { launch_bwd_small(s->ctx, lp.small_begin, lp.small_end, st); count++; }
+        if (lp.solve_end > lp.solve_begin) { Scope sc(s, 9); launch_bwd_gemv(s->ctx, lp.solve_begin, lp.solve_end, st); count++; }
+        if (lp.piece_end > lp.piece_begin) { Scope sc(s, 10); launch_bwd_trsv(s->ctx, lp.piece_begin, lp.piece_end, st); count++; }
+        if (lp.small_end > lp.small_begin) { Scope sc(s, 11); launch_bwd_small(s->ctx, lp.small_begin, lp.small_end, st); count++; }
     }
-    if (s->system == TLPB200_K1) launch_k1_recover(s->ctx, s->mat, s->d_d, xid, dx, dy, st);
-    else launch_k2_recover(s->ctx, s->mat, dx, dy, st);
+    {
+        Scope sc(s, 5);
+        if (s->system == TLPB200_K1) launch_k1_recover(s->ctx, s->mat, s->d_d, xid, dx, dy, st);
+        else launch_k2_recover(s->ctx, s->mat, dx, dy, st);
+    }
     count++;
     CK(cudaGetLastError());
 }
@@ -222,6 +271,7 @@ int finish_update(tlpb200_solver* s, int64_t* bad_pivot) {
         CK(cudaEventElapsedTime(&b, s->ev[1], s->ev[2]));
         s->ms_assemble = a;
         s->ms_factor = b;
+        collect_profile(s, true);
     }
     const int32_t info = *s->h_info;
     s->bad_pivot = (info >= 0 && info < s->sym.N) ? info : -1;
@@ -505,6 +555,7 @@ int tlpb200_solve(tlpb200_solver* s, double* dx, double* dy, const double* xi_p,
                 float a = 0;
                 CK(cudaEventElapsedTime(&a, s->ev[0], s->ev[3]));
                 s->ms_solve = a;
+                collect_profile(s, false);
             }
             std::memcpy(dx + (size_t)r * ldx, hout, n * 8);
             std::memcpy(dy + (size_t)r * ldy, hout + n, m * 8);
@@ -580,6 +631,9 @@ int tlpb200_stats_get(const tlpb200_solver* s, tlpb200_stats* o) {
     o->n_update = s->n_update;
     o->n_solve = s->n_solve;
     o->bytes_device = (int64_t)s->bytes_device;
+    o->flops_update_inner = s->plan.flops_update_inner;
+    o->flops_update_ext = s->plan.flops_update_ext;
+    for (int c = 0; c < 16; ++c) { o->ms_class[c] = s->ms_class[c]; o->n_class[c] = s->n_class[c]; }
     return TLPB200_OK;
 }
 
@@ -647,6 +701,7 @@ void tlpb200_destroy(tlpb200_solver* s) {
         if (s->h_pin) cudaFreeHost(s->h_pin);
         if (s->h_info) cudaFreeHost(s->h_info);
         for (auto& ev : s->ev) if (ev) cudaEventDestroy(ev);
+        for (auto& ev : s->pool) cudaEventDestroy(ev);
         if (s->own_stream) cudaStreamDestroy(s->own_stream);
     }
     delete s;
