@@ -237,9 +237,9 @@ def gpu_arm(args):
     kkt.set_profiling(False)
     cls = dict(zip(pkg._lib.KERNEL_CLASSES, zip(sp["ms_class"], sp["n_class"])))
     peaks, peak_src = measured_peaks()
-    ms_upd = cls["update_inner"][0] + cls["update_ext"][0]
-    n_upd = cls["update_inner"][1] + cls["update_ext"][1]
-    flops_upd = sp["flops_update_inner"] + sp["flops_update_ext"]
+    ms_upd = cls["update"][0] + cls["update128"][0]
+    n_upd = cls["update"][1] + cls["update128"][1]
+    flops_upd = sp["flops_update_ext"]
     # measured FP64 GEMM ceiling (cuBLAS DGEMM through torch), same spirit as MEASURED_PEAKS' bf16 number
     a = torch.randn(4096, 4096, dtype=torch.float64, device=dev); b = torch.randn(4096, 4096, dtype=torch.float64, device=dev)
     best = 1e9
@@ -263,7 +263,7 @@ def gpu_arm(args):
                 "launches_per_step": int(n_upd), "avg_launch_ms": round(ms_upd / max(1, n_upd), 4),
                 "algorithmic_flops_per_step": flops_upd, "share_of_update_ms": round(ms_upd / max(1e-9, sp["ms_assemble"] + sp["ms_factor"]), 3)}
     solve_bytes = 16.0 * sp["nnzL_stored"] if sp["nnzL_stored"] else 0.0
-    ms_tri = sum(cls[k][0] for k in ("fwd_small", "fwd_trsv", "fwd_gemv", "bwd_gemv", "bwd_trsv", "bwd_small"))
+    ms_tri = sum(cls[k][0] for k in ("fwd_small", "fwd_large", "bwd_large", "bwd_small"))
     roofline_solve = {"kernel": "supernodal forward+backward sweep (one rhs)", "bound": "hbm",
                       "achieved": round(16.0 * sp["nnzL"] / (ms_tri * 1e-3) / 1e9, 1) if ms_tri > 0 else None,
                       "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
@@ -284,6 +284,8 @@ def gpu_arm(args):
         "e2e": {"value": round(world * K / e2e_time, 4), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": round(e2e_time * 1e3 / K, 4)},
         "gpu_launches": launches,
+        "update_ms_host_api": round(float(np.mean([r["t_update"] for r in timed])) * 1e3, 3),
+        "solve_ms_host_api": round(float(np.sum([r["t_solve"] for r in timed]) / np.sum([len(r["rhs"]) for r in timed])) * 1e3, 3),
         "roofline": roofline, "roofline_solve": roofline_solve, "phases_one_step": phases,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -322,6 +324,10 @@ def reference_arm(args):
         return
     pkg, lp, sysname = build_lp(args.config)
     from oracle import cpu_kkt, hsd_ref
+    # the reference runs its own vector work with BLAS threads = 1 (model.jl:73); the factorisation's BLAS
+    # (SciPy's OpenBLAS, a separate library instance) gets every core below.
+    from threadpoolctl import threadpool_limits
+    threadpool_limits(limits=1, user_api="blas")
     A = lp.A
     sy = pkg.K1() if sysname == "K1" else pkg.K2()
     an = pkg.setup(A, sy, pkg.Backend(analyze_only=True))       # integer analysis only, no device

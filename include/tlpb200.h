@@ -44,7 +44,7 @@ enum { TLPB200_K1 = 1, TLPB200_K2 = 2 }; /* src/KKT/systems.jl:32 (K2), :54 (K1)
 typedef struct tlpb200_options {
     int32_t ordering;      /* 0 natural, 1 approximate minimum degree (default 1) */
     int32_t device;        /* CUDA device ordinal (default 0) */
-    int32_t piece_width;   /* column-piece width for wide supernodes (default 128; multiple of 64) */
+    int32_t piece_width;   /* column-piece width of wide supernodes (fixed: 128) */
     int32_t small_elems;   /* supernodes with nrow*ncol <= this run in the one-CTA kernels (default 4096) */
     int32_t relax_always;  /* amalgamation: always merge when merged width <= this (default 8) */
     int32_t use_graph;     /* 1 = replay update!/solve! as CUDA graphs (default 1) */
@@ -67,12 +67,12 @@ typedef struct tlpb200_stats {
     int64_t bad_pivot;      /* permuted column of the first bad pivot of the last update!, -1 if none */
     int64_t n_update, n_solve;
     int64_t bytes_device;
-    /* algorithmic flops (2 per multiply-add, lower triangle only) of the tile-update kernel launches of
-     * one update!: inside column pieces (incl. the fused 64x64 potrf) / to the rest of the matrix */
+    /* algorithmic flops of one update! (2 per multiply-add, lower triangle only): diagonal-block
+     * factor + trsm of the column pieces / tile-update kernel (supernode SYRK-GEMM + scatter) */
     double flops_update_inner, flops_update_ext;
     /* profiling mode: CUDA-event time and launch count per kernel class of the last update!/solve!
-     * 0 assemble  1 small_factor  2 update_inner  3 trsm  4 update_ext  5 rhs+recover
-     * 6 fwd_small 7 fwd_trsv 8 fwd_gemv 9 bwd_gemv 10 bwd_trsv 11 bwd_small */
+     * 0 assemble  1 small_factor  2 diag_factor  3 trsm  4 update  5 rhs+recover
+     * 6 fwd_small 7 fwd_large 8 -  9 bwd_large 10 invert_diag 11 bwd_small */
     double ms_class[16];
     int64_t n_class[16];
 } tlpb200_stats;

@@ -44,8 +44,8 @@ class Stats(C.Structure):
         return d
 
 
-KERNEL_CLASSES = ["assemble", "small_factor", "update_inner", "trsm", "update_ext", "rhs_recover",
-                  "fwd_small", "fwd_trsv", "fwd_gemv", "bwd_gemv", "bwd_trsv", "bwd_small"]
+KERNEL_CLASSES = ["assemble", "small_factor", "diag_factor", "trsm", "update", "rhs_recover",
+                  "fwd_small", "fwd_large", "update128", "bwd_large", "invert_diag", "bwd_small"]
 
 
 # every symbol include/tlpb200.h declares (tests check that the library exports all of them)

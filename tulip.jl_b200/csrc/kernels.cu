@@ -23,6 +23,21 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                  : "d"(a), "d"(b));
 }
 
+__device__ __forceinline__ int32_t ld_acquire(const int32_t* p) {
+    int32_t v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int32_t* p, int32_t v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
 __device__ __forceinline__ int32_t pos_in_target(const DevCtx& c, int32_t t, int32_t gi) {
     const int32_t f = c.sn_first[t], l = c.sn_first[t + 1];
     if (gi < l) return gi - f;
@@ -40,34 +55,6 @@ __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
-}
-
-// In-shared signed Cholesky of an nk x nk block stored column-major with leading dimension ldc.
-// sg[j] = expected sign of pivot j.  Bad pivots (wrong sign / zero / NaN) are recorded in info
-// and replaced by a unit pivot so that the kernel always terminates with finite data.
-__device__ void potrf_shared(double* Cs, int ldc, int nk, const double* sg, int32_t* info, int32_t gcol0, int nthr) {
-    const int tid = threadIdx.x;
-    for (int j = 0; j < nk; ++j) {
-        __syncthreads();
-        double d = Cs[j * ldc + j];
-        const double sj = sg[j];
-        if (!(d * sj > 0.0)) {
-            if (tid == 0) atomicMin(info, gcol0 + j);
-            d = sj;
-        }
-        const double ljj = sqrt(d * sj);
-        const double inv = 1.0 / (sj * ljj);
-        __syncthreads();
-        for (int i = j + 1 + tid; i < nk; i += nthr) Cs[j * ldc + i] *= inv;
-        if (tid == 0) Cs[j * ldc + j] = ljj;
-        __syncthreads();
-        const int rem = nk - j - 1;
-        for (int e = tid; e < rem * rem; e += nthr) {
-            const int k = j + 1 + e / rem, i = j + 1 + e % rem;
-            if (i >= k) Cs[k * ldc + i] -= Cs[j * ldc + i] * sj * Cs[j * ldc + k];
-        }
-    }
-    __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -181,184 +168,51 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_small_factor(DevCtx c, int32_
 }
 
 // ------------------------------------------------------------------------------------------
-// tile update:  C_tgt[pos(I), cols(K)] -= L[I, 0:kdim] * S * L[K, 0:kdim]'   (FP64 DMMA m8n8k4)
-// 64x64 output tile per CTA, 4 warps, each warp a 32x32 sub-tile (4x4 mma tiles).
-// diag = 1: keep only row >= col.  diag = 2: additionally factor the nk x nk diagonal block.
+// explicit inverses of the 128x128 diagonal blocks (used by the dense solve kernels):
+// thread c computes column c of X = L^{-1} by forward substitution.
 // ------------------------------------------------------------------------------------------
-constexpr int UPD_THREADS = 128;
-constexpr int KC = 16;
-constexpr int LDT = TILE + 4;   // 68: conflict-free fragment loads (68 mod 16 == 4)
-constexpr int LDC = TILE + 1;
+constexpr int INV_THREADS = SBLK;
 
-__global__ void __launch_bounds__(UPD_THREADS) k_update(DevCtx c, int32_t begin, int atomic) {
-    __shared__ double sm[2 * 2 * KC * LDT];      // As[2][KC][LDT], Bs[2][KC][LDT]; reused as Cs[64][65]
-    __shared__ int32_t tpos[TILE];
-    __shared__ int64_t tcol[TILE];
-    __shared__ double sgn[TILE];
-
-    const UpdTask T = c.upd[begin + blockIdx.x];
-    const Piece pc = c.pieces[T.piece];
-    const int32_t s = pc.sn;
+__global__ void __launch_bounds__(INV_THREADS) k_invert_diag(DevCtx c) {
+    extern __shared__ double smem_d[];
+    double* Cs = smem_d;                 // [SBLK][SBLK+1] column-major: L on entry, X = L^{-1} on exit
+    const int LDI = SBLK + 1;
+    const int32_t b = blockIdx.x;
+    const int32_t s = c.dblk_sn[b], bi = c.dblk_idx[b];
     const int32_t f = c.sn_first[s];
-    const int64_t rp = c.sn_rowptr[s];
-    const int32_t ld = (int32_t)(c.sn_rowptr[s + 1] - rp);
-    const int32_t* rows = c.sn_rows + rp;
-    const double* panel = c.Lx + c.sn_xptr[s] + (int64_t)(pc.c0 - f) * ld;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wr = warp >> 1, wc = warp & 1, g = lane >> 2, t4 = lane & 3;
-
-    // target addressing
-    const int32_t t = T.tgt;
-    const int32_t ft = c.sn_first[t];
-    const int64_t ldt = c.sn_rowptr[t + 1] - c.sn_rowptr[t];
-    if (tid < TILE) {
-        int32_t p = 0;
-        if (tid < T.ni) p = (t == s) ? (T.i0 + tid) : pos_in_target(c, t, rows[T.i0 + tid]);
-        tpos[tid] = p;
-    } else {
-        const int kk = tid - TILE;
-        tcol[kk] = (kk < T.nk) ? (int64_t)(rows[T.k0 + kk] - ft) * ldt : 0;
-        sgn[kk] = (kk < T.nk && T.diag == 2) ? (double)c.sign[f + T.k0 + kk] : 1.0;
-    }
-
-    double acc[4][4][2];
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
-
-    double (*As)[KC][LDT] = reinterpret_cast<double (*)[KC][LDT]>(sm);
-    double (*Bs)[KC][LDT] = reinterpret_cast<double (*)[KC][LDT]>(sm + 2 * KC * LDT);
-
-    const int nch = (T.kdim + KC - 1) / KC;
-    double ra[8], rb[8];
-    auto load_regs = [&](int ch) {
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            const int e = tid + UPD_THREADS * r;
-            const int row = e & (TILE - 1), kk = ch * KC + (e >> 6);
-            const bool kv = kk < T.kdim;
-            const double* col = panel + (int64_t)kk * ld;
-            ra[r] = (kv && row < T.ni) ? col[T.i0 + row] : 0.0;
-            rb[r] = (kv && row < T.nk) ? col[T.k0 + row] * (double)c.sign[pc.c0 + kk] : 0.0;
-        }
-    };
-    auto store_smem = [&](int st) {
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            const int e = tid + UPD_THREADS * r;
-            As[st][e >> 6][e & (TILE - 1)] = ra[r];
-            Bs[st][e >> 6][e & (TILE - 1)] = rb[r];
-        }
-    };
-    if (nch > 0) {
-        load_regs(0);
-        store_smem(0);
-    }
-    __syncthreads();
-    for (int ch = 0; ch < nch; ++ch) {
-        const int st = ch & 1;
-        if (ch + 1 < nch) load_regs(ch + 1);
-#pragma unroll
-        for (int k4 = 0; k4 < KC; k4 += 4) {
-            double a[4], b[4];
-#pragma unroll
-            for (int mi = 0; mi < 4; ++mi) a[mi] = As[st][k4 + t4][wr * 32 + mi * 8 + g];
-#pragma unroll
-            for (int nj = 0; nj < 4; ++nj) b[nj] = Bs[st][k4 + t4][wc * 32 + nj * 8 + g];
-#pragma unroll
-            for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-                for (int nj = 0; nj < 4; ++nj) dmma884(acc[mi][nj][0], acc[mi][nj][1], a[mi], b[nj]);
-        }
-        if (ch + 1 < nch) store_smem(st ^ 1);
-        __syncthreads();
-    }
-
-    double* Tx = c.Lx + c.sn_xptr[t];
-    if (T.diag != 2) {
-#pragma unroll
-        for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-            for (int nj = 0; nj < 4; ++nj)
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int ii = wr * 32 + mi * 8 + g, kk = wc * 32 + nj * 8 + t4 * 2 + e;
-                    if (ii < T.ni && kk < T.nk && (T.diag == 0 || ii >= kk)) {
-                        double* p = Tx + tcol[kk] + tpos[ii];
-                        if (atomic) atomicAdd(p, -acc[mi][nj][e]); else *p -= acc[mi][nj][e];
-                    }
-                }
-        return;
-    }
-    // diag == 2: rows >= nk of the tile are ordinary updates; the nk x nk block is updated in
-    // shared memory, factored there and written back (target is the own panel: positions direct)
-    double* Cs = sm;
-    for (int e = tid; e < T.nk * T.nk; e += UPD_THREADS) {
-        const int kk = e / T.nk, ii = e % T.nk;
-        Cs[kk * LDC + ii] = (ii >= kk) ? Tx[tcol[kk] + tpos[ii]] : 0.0;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-        for (int nj = 0; nj < 4; ++nj)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int ii = wr * 32 + mi * 8 + g, kk = wc * 32 + nj * 8 + t4 * 2 + e;
-                if (ii < T.ni && kk < T.nk && ii >= kk) {
-                    if (ii < T.nk) Cs[kk * LDC + ii] -= acc[mi][nj][e];
-                    else Tx[tcol[kk] + tpos[ii]] -= acc[mi][nj][e];
-                }
-            }
-    potrf_shared(Cs, LDC, T.nk, sgn, c.info, f + T.k0, UPD_THREADS);
-    for (int e = tid; e < T.nk * T.nk; e += UPD_THREADS) {
-        const int kk = e / T.nk, ii = e % T.nk;
-        if (ii >= kk) Tx[tcol[kk] + tpos[ii]] = Cs[kk * LDC + ii];
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// trsm: rows below a factored 64-wide diagonal block:  X = A21 * L11^{-T} * S   (one row / thread)
-// ------------------------------------------------------------------------------------------
-constexpr int TRSM_THREADS = 2 * TILE;
-
-__global__ void __launch_bounds__(TRSM_THREADS) k_trsm(DevCtx c, int32_t begin) {
-    __shared__ double Ls[TILE][TILE];    // Ls[j][k] = L11[j,k] * s_k  (k < j)
-    __shared__ double invd[TILE];        // 1 / (s_j * L11[j,j])
-    const PanelTask T = c.panel[begin + blockIdx.x];
-    const Piece pc = c.pieces[T.piece];
-    const int32_t s = pc.sn;
-    const int32_t f = c.sn_first[s];
+    const int32_t nc = c.sn_first[s + 1] - f;
     const int32_t ld = (int32_t)(c.sn_rowptr[s + 1] - c.sn_rowptr[s]);
-    const int32_t kb = (pc.c0 - f) + T.step * TILE;                       // local column of the block
-    const int32_t nb = min(TILE, (pc.c1 - pc.c0) - T.step * TILE);
-    double* X = c.Lx + c.sn_xptr[s];
+    const int32_t lc0 = bi * SBLK, nb = min(SBLK, nc - lc0);
+    const double* D = c.Lx + c.sn_xptr[s] + (int64_t)lc0 * ld + lc0;
     const int tid = threadIdx.x;
-
-    for (int e = tid; e < TILE * TILE; e += TRSM_THREADS) {
-        const int j = e / TILE, k = e % TILE;
+    for (int k = 0; k < nb; ++k)
+        if (tid < nb) Cs[k * LDI + tid] = (tid >= k) ? D[(int64_t)k * ld + tid] : 0.0;
+    // in-place inverse of a lower-triangular matrix, last column first:
+    // X[j,j] = 1/L[j,j];  X[i,j] = -X[j,j] * sum_{k=j+1..i} X[i,k] L[k,j]   (i > j)
+    for (int j = nb - 1; j >= 0; --j) {
+        __syncthreads();
+        const double xjj = 1.0 / Cs[j * LDI + j];
         double v = 0.0;
-        if (j < nb && k < j) v = X[(int64_t)(kb + k) * ld + kb + j] * (double)c.sign[f + kb + k];
-        Ls[j][k] = v;
+        if (tid > j && tid < nb) {
+            double a = 0.0;
+            for (int k = j + 1; k <= tid; ++k) a += Cs[k * LDI + tid] * Cs[j * LDI + k];
+            v = -a * xjj;
+        }
+        __syncthreads();
+        if (tid > j && tid < nb) Cs[j * LDI + tid] = v;
+        if (tid == j) Cs[j * LDI + j] = xjj;
     }
-    if (tid < TILE) invd[tid] = (tid < nb) ? 1.0 / ((double)c.sign[f + kb + tid] * X[(int64_t)(kb + tid) * ld + kb + tid]) : 1.0;
     __syncthreads();
-    if (tid >= T.nr) return;
-    const int32_t r = T.r0 + tid;
-    double x[TILE];
-#pragma unroll
-    for (int j = 0; j < TILE; ++j) x[j] = (j < nb) ? X[(int64_t)(kb + j) * ld + r] : 0.0;
-#pragma unroll
-    for (int j = 0; j < TILE; ++j) {
-        double a = x[j];
-#pragma unroll
-        for (int k = 0; k < j; ++k) a -= x[k] * Ls[j][k];
-        x[j] = a * invd[j];
+    double* out = c.Dinv + (int64_t)b * SBLK * SBLK;
+    double* outT = c.DinvT + (int64_t)b * SBLK * SBLK;
+    for (int e = tid; e < SBLK * SBLK; e += INV_THREADS) {
+        const int cc = e / SBLK, r = e % SBLK;
+        out[cc * SBLK + r] = (cc < nb && r < nb && r >= cc) ? Cs[cc * LDI + r] : 0.0;     // Dinv  (column cc, row r)
     }
-#pragma unroll
-    for (int j = 0; j < TILE; ++j)
-        if (j < nb) X[(int64_t)(kb + j) * ld + r] = x[j];
+    for (int e = tid; e < SBLK * SBLK; e += INV_THREADS) {
+        const int r = e / SBLK, cc = e % SBLK;
+        outT[r * SBLK + cc] = (cc < nb && r < nb && r >= cc) ? Cs[cc * LDI + r] : 0.0;    // DinvT (column r, row cc) = X[r, cc]
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -424,112 +278,174 @@ __global__ void __launch_bounds__(32 * SOLVE_SMALL_WARPS) k_bwd_small(DevCtx c, 
     if (lane < nc) c.wk[f + lane] = t;
 }
 
-// wide pieces: diagonal block (w <= 128) staged in shared memory
-constexpr int TRSV_THREADS = 128;
+// ---- dense block solve of the non-small supernodes ----------------------------------------------
+// Persistent CTAs (<= one per SM, all co-resident) walk a wavefront-ordered item list; a diagonal
+// block publishes its solution through a release/acquire flag, consumers spin on it.  Each item
+// streams its 128x128 tiles of L exactly once (the HBM-roofline traffic of a triangular solve).
+constexpr int SL_THREADS = 512;
+constexpr int SL_CG = SL_THREADS / SBLK;   // 4 column groups of 32
 
-__device__ __forceinline__ void load_diag_block(const DevCtx& c, const Piece& pc, double* Ls, double* invd, int W1) {
-    const int32_t s = pc.sn;
-    const int32_t f = c.sn_first[s];
-    const int32_t ld = (int32_t)(c.sn_rowptr[s + 1] - c.sn_rowptr[s]);
-    const int32_t lc0 = pc.c0 - f, w = pc.c1 - pc.c0;
-    const double* L = c.Lx + c.sn_xptr[s] + (int64_t)lc0 * ld + lc0;
-    for (int e = threadIdx.x; e < w * w; e += blockDim.x) {
-        const int k = e / w, i = e % w;
-        if (i >= k) Ls[k * W1 + i] = L[(int64_t)k * ld + i];
+__device__ __forceinline__ void wait_flag(const int32_t* flag) {
+    if (threadIdx.x == 0) {
+        while (ld_acquire(flag) == 0) { }
     }
     __syncthreads();
-    for (int j = threadIdx.x; j < w; j += blockDim.x) invd[j] = 1.0 / Ls[j * W1 + j];
 }
 
-__global__ void __launch_bounds__(TRSV_THREADS) k_fwd_trsv(DevCtx c, int32_t begin) {
+__global__ void __launch_bounds__(SL_THREADS, 1) k_fwd_large(DevCtx c, int32_t begin, int32_t end) {
     extern __shared__ double smem_d[];
-    const Piece pc = c.pieces[c.level_pieces[begin + blockIdx.x]];
-    const int w = pc.c1 - pc.c0, W1 = w + 1;
-    double* Ls = smem_d;
-    double* invd = Ls + w * W1;
-    double* bs = invd + w;
-    double* us = bs + w;
-    const int tid = threadIdx.x;
-    for (int i = tid; i < w; i += TRSV_THREADS) bs[i] = c.wk[pc.c0 + i];
-    load_diag_block(c, pc, Ls, invd, W1);
-    for (int j = 0; j < w; ++j) {
+    double* Ds = smem_d;                   // [SBLK*SBLK] explicit inverse of the item's diagonal block
+    double* xs = Ds + SBLK * SBLK;         // [SBLK]
+    double* red = xs + SBLK;               // [SL_CG][SBLK]
+    const int tid = threadIdx.x, r = tid & (SBLK - 1), cg = tid >> 7;
+    int32_t* fflag = c.flags;
+    for (int32_t it = begin + blockIdx.x; it < end; it += gridDim.x) {
+        const SolveItem I = c.fwd_items[it];
+        const int32_t s = I.sn;
+        const int32_t f = c.sn_first[s];
+        const int32_t nc = c.sn_first[s + 1] - f;
+        const int64_t rp = c.sn_rowptr[s];
+        const int32_t ld = (int32_t)(c.sn_rowptr[s + 1] - rp);
+        const double* panel = c.Lx + c.sn_xptr[s];
+        const int32_t db = c.sn_dblk[s];
+        const int32_t ncb = (nc + SBLK - 1) / SBLK;
+        const int32_t njt = (I.kind == 0) ? I.blk : ncb;
+        const bool rvalid = r < I.nr;
+        const int32_t prow = I.r0 + (rvalid ? r : 0);
+        if (I.kind == 0) {   // stage the inverse of the diagonal block (needed last)
+            const double* src = c.Dinv + (int64_t)(db + I.blk) * SBLK * SBLK;
+            for (int e = tid; e < SBLK * SBLK / 2; e += SL_THREADS) cp_async16(Ds + 2 * e, src + 2 * e);
+            cp_async_commit();
+        }
+        double t[32];
+        double acc = 0.0;
+        auto load_tile = [&](int j) {
+            const int32_t nbj = min(SBLK, nc - j * SBLK);
+            const double* col = panel + (int64_t)(j * SBLK + cg * 32) * ld + prow;
+#pragma unroll
+            for (int cc = 0; cc < 32; ++cc) t[cc] = (rvalid && cg * 32 + cc < nbj) ? col[(int64_t)cc * ld] : 0.0;
+        };
+        if (njt > 0) load_tile(0);
+        for (int j = 0; j < njt; ++j) {
+            wait_flag(fflag + db + j);
+            if (tid < SBLK) xs[tid] = (j * SBLK + tid < nc) ? __ldcg(c.wk + f + j * SBLK + tid) : 0.0;
+            __syncthreads();
+#pragma unroll
+            for (int cc = 0; cc < 32; ++cc) acc -= t[cc] * xs[cg * 32 + cc];
+            if (j + 1 < njt) load_tile(j + 1);
+            __syncthreads();      // xs is rewritten in the next round
+        }
+        red[cg * SBLK + r] = acc;
         __syncthreads();
-        const double uj = bs[j] * invd[j];
-        if (tid == 0) us[j] = uj;
-        for (int i = j + 1 + tid; i < w; i += TRSV_THREADS) bs[i] -= Ls[j * W1 + i] * uj;
+        if (I.kind == 1) {
+            if (tid < SBLK && rvalid) {
+                const double v = red[r] + red[SBLK + r] + red[2 * SBLK + r] + red[3 * SBLK + r];
+                atomicAdd(c.wk + c.sn_rows[rp + I.r0 + r], v);
+            }
+            __syncthreads();
+            continue;
+        }
+        if (tid < SBLK)
+            xs[tid] = rvalid ? (__ldcg(c.wk + f + I.r0 + tid) + red[tid] + red[SBLK + tid] + red[2 * SBLK + tid] + red[3 * SBLK + tid]) : 0.0;
+        cp_async_wait_all();
+        __syncthreads();
+        double a2 = 0.0;
+#pragma unroll
+        for (int cc = 0; cc < 32; ++cc) a2 += Ds[(cg * 32 + cc) * SBLK + r] * xs[cg * 32 + cc];
+        __syncthreads();
+        red[cg * SBLK + r] = a2;
+        __syncthreads();
+        if (tid < SBLK && rvalid)
+            __stcg(c.wk + f + I.r0 + tid, red[tid] + red[SBLK + tid] + red[2 * SBLK + tid] + red[3 * SBLK + tid]);
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) st_release(fflag + db + I.blk, 1);
     }
-    __syncthreads();
-    for (int i = tid; i < w; i += TRSV_THREADS) c.wk[pc.c0 + i] = us[i];
 }
 
-__global__ void __launch_bounds__(SOLVE_ROWS) k_fwd_gemv(DevCtx c, int32_t begin) {
-    __shared__ double us[128];
-    const SolveTask T = c.solve[begin + blockIdx.x];
-    const Piece pc = c.pieces[T.piece];
-    const int32_t s = pc.sn;
-    const int32_t f = c.sn_first[s];
-    const int64_t rp = c.sn_rowptr[s];
-    const int32_t ld = (int32_t)(c.sn_rowptr[s + 1] - rp);
-    const int w = pc.c1 - pc.c0;
-    const double* L = c.Lx + c.sn_xptr[s] + (int64_t)(pc.c0 - f) * ld;
-    const int tid = threadIdx.x;
-    if (tid < w) us[tid] = c.wk[pc.c0 + tid];
-    __syncthreads();
-    if (tid >= T.nr) return;
-    const int32_t r = T.r0 + tid;
-    double a = 0.0;
-#pragma unroll 4
-    for (int k = 0; k < w; ++k) a += L[(int64_t)k * ld + r] * us[k];
-    atomicAdd(c.wk + c.sn_rows[rp + r], -a);
-}
-
-__global__ void __launch_bounds__(SOLVE_ROWS) k_bwd_gemv(DevCtx c, int32_t begin) {
-    __shared__ double sacc[128];
-    const SolveTask T = c.solve[begin + blockIdx.x];
-    const Piece pc = c.pieces[T.piece];
-    const int32_t s = pc.sn;
-    const int32_t f = c.sn_first[s];
-    const int64_t rp = c.sn_rowptr[s];
-    const int32_t ld = (int32_t)(c.sn_rowptr[s + 1] - rp);
-    const int w = pc.c1 - pc.c0;
-    const double* L = c.Lx + c.sn_xptr[s] + (int64_t)(pc.c0 - f) * ld;
-    const int tid = threadIdx.x, lane = tid & 31;
-    if (tid < 128) sacc[tid] = 0.0;
-    __syncthreads();
-    const bool valid = tid < T.nr;
-    const int32_t r = T.r0 + tid;
-    const double xr = valid ? c.wk[c.sn_rows[rp + r]] : 0.0;
-    for (int k = 0; k < w; ++k) {
-        double v = valid ? L[(int64_t)k * ld + r] * xr : 0.0;
-        v = warp_sum(v);
-        if (lane == 0) atomicAdd(&sacc[k], v);
-    }
-    __syncthreads();
-    if (tid < w) atomicAdd(c.acc + pc.c0 + tid, sacc[tid]);
-}
-
-__global__ void __launch_bounds__(TRSV_THREADS) k_bwd_trsv(DevCtx c, int32_t begin) {
+__global__ void __launch_bounds__(SL_THREADS, 1) k_bwd_large(DevCtx c, int32_t begin, int32_t end) {
     extern __shared__ double smem_d[];
-    const Piece pc = c.pieces[c.level_pieces[begin + blockIdx.x]];
-    const int w = pc.c1 - pc.c0, W1 = w + 1;
-    double* Ls = smem_d;
-    double* invd = Ls + w * W1;
-    double* ts = invd + w;
-    double* xs = ts + w;
-    const int tid = threadIdx.x;
-    for (int i = tid; i < w; i += TRSV_THREADS) {
-        ts[i] = (double)c.sign[pc.c0 + i] * c.wk[pc.c0 + i] - c.acc[pc.c0 + i];
-        c.acc[pc.c0 + i] = 0.0;
-    }
-    load_diag_block(c, pc, Ls, invd, W1);
-    for (int j = w - 1; j >= 0; --j) {
+    double* Ds = smem_d;                   // [SBLK*SBLK] transposed inverse of the item's diagonal block
+    double* xs = Ds + SBLK * SBLK;         // [SBLK]
+    double* red = xs + SBLK;               // [SL_CG][SBLK]
+    const int tid = threadIdx.x, r = tid & (SBLK - 1), cg = tid >> 7, lane = tid & 31, wq = (tid >> 5) & 3;
+    int32_t* bflag = c.flags + c.ndblk;
+    for (int32_t it = begin + blockIdx.x; it < end; it += gridDim.x) {
+        const SolveItem I = c.bwd_items[it];
+        const int32_t s = I.sn;
+        const int32_t f = c.sn_first[s];
+        const int32_t nc = c.sn_first[s + 1] - f;
+        const int64_t rp = c.sn_rowptr[s];
+        const int32_t ld = (int32_t)(c.sn_rowptr[s + 1] - rp);
+        const int32_t nrow = ld;
+        const double* panel = c.Lx + c.sn_xptr[s];
+        const int32_t db = c.sn_dblk[s];
+        const int32_t ncb = (nc + SBLK - 1) / SBLK;
+        const int32_t i = I.blk;
+        {
+            const double* src = c.DinvT + (int64_t)(db + i) * SBLK * SBLK;
+            for (int e = tid; e < SBLK * SBLK / 2; e += SL_THREADS) cp_async16(Ds + 2 * e, src + 2 * e);
+            cp_async_commit();
+        }
+        // p[cc] accumulates sum_r L[r, i*128 + cg*32 + cc] * x[r] over this thread's rows r (mod 128)
+        double p[32];
+#pragma unroll
+        for (int cc = 0; cc < 32; ++cc) p[cc] = 0.0;
+        const double* colbase = panel + (int64_t)(i * SBLK + cg * 32) * ld;
+        const int32_t ncv = min(32, max(0, I.nr - cg * 32));     // valid columns of this group
+        // rows below the supernode's columns: their x is final (ancestors were solved earlier)
+        for (int32_t r0 = nc; r0 < nrow; r0 += SBLK) {
+            const int32_t rr = r0 + r;
+            if (rr < nrow) {
+                const double xr = __ldcg(c.wk + c.sn_rows[rp + rr]);
+#pragma unroll
+                for (int cc = 0; cc < 32; ++cc)
+                    if (cc < ncv) p[cc] += colbase[(int64_t)cc * ld + rr] * xr;
+            }
+        }
+        // later diagonal blocks of the same supernode, nearest last (it is the one we wait for)
+        for (int32_t j = ncb - 1; j > i; --j) {
+            wait_flag(bflag + db + j);
+            const int32_t rr = j * SBLK + r;
+            if (rr < nc) {
+                const double xr = __ldcg(c.wk + f + rr);
+#pragma unroll
+                for (int cc = 0; cc < 32; ++cc)
+                    if (cc < ncv) p[cc] += colbase[(int64_t)cc * ld + rr] * xr;
+            }
+        }
+        // reduce over the 32 rows of the warp: lane l ends with the sum of column l of its group
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            const bool up = (lane & off) != 0;
+#pragma unroll
+            for (int k = 0; k < off; ++k) {
+                const double send = up ? p[k] : p[k + off];
+                const double keep = up ? p[k + off] : p[k];
+                p[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            }
+        }
         __syncthreads();
-        const double xj = ts[j] * invd[j];
-        if (tid == 0) xs[j] = xj;
-        for (int i = tid; i < j; i += TRSV_THREADS) ts[i] -= Ls[i * W1 + j] * xj;
+        red[wq * SBLK + cg * 32 + lane] = p[0];          // 4 warps (row quarters) per column group
+        __syncthreads();
+        if (tid < SBLK)
+            xs[tid] = (tid < I.nr) ? ((double)c.sign[f + i * SBLK + tid] * __ldcg(c.wk + f + i * SBLK + tid)
+                                      - (red[tid] + red[SBLK + tid] + red[2 * SBLK + tid] + red[3 * SBLK + tid])) : 0.0;
+        cp_async_wait_all();
+        __syncthreads();
+        // x = X' * tmp : row r of X' is column r of X; Ds holds X' column-major -> Ds[col*128 + row]
+        double a2 = 0.0;
+#pragma unroll
+        for (int cc = 0; cc < 32; ++cc) a2 += Ds[(cg * 32 + cc) * SBLK + r] * xs[cg * 32 + cc];
+        __syncthreads();
+        red[cg * SBLK + r] = a2;
+        __syncthreads();
+        if (tid < SBLK && tid < I.nr)
+            __stcg(c.wk + f + i * SBLK + tid, red[tid] + red[SBLK + tid] + red[2 * SBLK + tid] + red[3 * SBLK + tid]);
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) st_release(bflag + db + i, 1);
     }
-    __syncthreads();
-    for (int i = tid; i < w; i += TRSV_THREADS) c.wk[pc.c0 + i] = xs[i];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -596,22 +512,28 @@ size_t small_factor_smem(int32_t max_elems, int32_t max_nrow) {
     return (size_t)max_elems * 8 + 64 * 8 + (size_t)max_nrow * 4 + 16;
 }
 
-static size_t trsv_smem(int w) { return ((size_t)w * (w + 1) + 3 * (size_t)w) * 8; }
+static constexpr size_t INV_SMEM = (size_t)SBLK * (SBLK + 1) * 8;
+static constexpr size_t SL_SMEM = ((size_t)SBLK * SBLK + SBLK + (size_t)SL_CG * SBLK) * 8;
 
-void kernels_static_init() {
-    cudaFuncSetAttribute(k_small_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    cudaFuncSetAttribute(k_fwd_trsv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsv_smem(128));
-    cudaFuncSetAttribute(k_bwd_trsv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsv_smem(128));
+#define SETATTR(k, bytes)                                                                                   \
+    do {                                                                                                    \
+        cudaError_t e_ = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)); \
+        if (e_ != cudaSuccess) return e_;                                                                   \
+    } while (0)
+
+cudaError_t kernels_static_init() {
+    SETATTR(k_small_factor, 96 * 1024);
+    SETATTR(k_invert_diag, INV_SMEM);
+    SETATTR(k_fwd_large, SL_SMEM);
+    SETATTR(k_bwd_large, SL_SMEM);
+    return factor_kernels_static_init();
 }
 
 void launch_small_factor(const DevCtx& c, int32_t begin, int32_t end, size_t smem, cudaStream_t st) {
     if (end > begin) k_small_factor<<<end - begin, SMALL_THREADS, smem, st>>>(c, begin);
 }
-void launch_update(const DevCtx& c, int32_t begin, int32_t end, int atomic, cudaStream_t st) {
-    if (end > begin) k_update<<<end - begin, UPD_THREADS, 0, st>>>(c, begin, atomic);
-}
-void launch_trsm(const DevCtx& c, int32_t begin, int32_t end, cudaStream_t st) {
-    if (end > begin) k_trsm<<<end - begin, TRSM_THREADS, 0, st>>>(c, begin);
+void launch_invert_diag(const DevCtx& c, cudaStream_t st) {
+    if (c.ndblk > 0) k_invert_diag<<<c.ndblk, INV_THREADS, INV_SMEM, st>>>(c);
 }
 void launch_fwd_small(const DevCtx& c, int32_t begin, int32_t end, cudaStream_t st) {
     if (end > begin) k_fwd_small<<<nblk(end - begin, SOLVE_SMALL_WARPS), 32 * SOLVE_SMALL_WARPS, 0, st>>>(c, begin, end);
@@ -619,17 +541,11 @@ void launch_fwd_small(const DevCtx& c, int32_t begin, int32_t end, cudaStream_t 
 void launch_bwd_small(const DevCtx& c, int32_t begin, int32_t end, cudaStream_t st) {
     if (end > begin) k_bwd_small<<<nblk(end - begin, SOLVE_SMALL_WARPS), 32 * SOLVE_SMALL_WARPS, 0, st>>>(c, begin, end);
 }
-void launch_fwd_trsv(const DevCtx& c, int32_t begin, int32_t end, cudaStream_t st) {
-    if (end > begin) k_fwd_trsv<<<end - begin, TRSV_THREADS, trsv_smem(128), st>>>(c, begin);
+void launch_fwd_large(const DevCtx& c, int32_t begin, int32_t end, int nsm, cudaStream_t st) {
+    if (end > begin) k_fwd_large<<<min(end - begin, nsm), SL_THREADS, SL_SMEM, st>>>(c, begin, end);
 }
-void launch_bwd_trsv(const DevCtx& c, int32_t begin, int32_t end, cudaStream_t st) {
-    if (end > begin) k_bwd_trsv<<<end - begin, TRSV_THREADS, trsv_smem(128), st>>>(c, begin);
-}
-void launch_fwd_gemv(const DevCtx& c, int32_t begin, int32_t end, cudaStream_t st) {
-    if (end > begin) k_fwd_gemv<<<end - begin, SOLVE_ROWS, 0, st>>>(c, begin);
-}
-void launch_bwd_gemv(const DevCtx& c, int32_t begin, int32_t end, cudaStream_t st) {
-    if (end > begin) k_bwd_gemv<<<end - begin, SOLVE_ROWS, 0, st>>>(c, begin);
+void launch_bwd_large(const DevCtx& c, int32_t begin, int32_t end, int nsm, cudaStream_t st) {
+    if (end > begin) k_bwd_large<<<min(end - begin, nsm), SL_THREADS, SL_SMEM, st>>>(c, begin, end);
 }
 void launch_k1_rhs(const DevCtx& c, const DevMat& A, const double* d, const double* xi_p, const double* xi_d,
                    cudaStream_t st) {

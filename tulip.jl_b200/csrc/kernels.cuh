@@ -27,14 +27,23 @@ struct DevCtx {
     const int32_t* small_list;
     const int32_t* level_pieces;
     const UpdTask* upd;
+    const UpdTask* upd_lazy;
     const PanelTask* panel;
-    const SolveTask* solve;
+    const SolveItem* fwd_items;
+    const SolveItem* bwd_items;
+    const int32_t* sn_dblk;    // [nsuper] first diagonal block of a non-small supernode
+    const int32_t* dblk_sn;    // [ndblk]
+    const int32_t* dblk_idx;   // [ndblk]
     // numeric state
     double* Lx;
+    double* Dinv;    // [ndblk][128*128] explicit inverses of the diagonal blocks (column-major, lower)
+    double* DinvT;   // [ndblk][128*128] their transposes (column-major, upper)
+    int32_t* flags;  // [2*ndblk] forward / backward "block solved" flags of the dense solve kernels
     int32_t* info;   // info[0] = smallest permuted column with a bad pivot (INT_MAX if none)
     double* wk;      // [N] work vector of the triangular solves (permuted order)
-    double* acc;     // [N] accumulator for the backward gemv of wide pieces (kept zero between uses)
     int32_t N;
+    int32_t ndblk;
+    int32_t has_neg;   // 1 when some pivots are expected negative (K2)
 };
 
 // matrix A on the device (CSC + CSR copies) and the assemble maps
@@ -62,15 +71,16 @@ void launch_assemble_k1(const DevCtx& c, const DevMat& A, const double* d, const
 void launch_assemble_k2(const DevCtx& c, const DevMat& A, const double* theta, const double* regP, const double* regD,
                         cudaStream_t st);
 void launch_small_factor(const DevCtx& c, int32_t begin, int32_t end, size_t smem, cudaStream_t st);
-void launch_update(const DevCtx& c, int32_t begin, int32_t end, int atomic, cudaStream_t st);
+void launch_diag_factor(const DevCtx& c, int32_t begin, int32_t end, cudaStream_t st);
 void launch_trsm(const DevCtx& c, int32_t begin, int32_t end, cudaStream_t st);
+void launch_update(const DevCtx& c, int32_t begin, int32_t end, int atomic, cudaStream_t st);
+void launch_update_lazy(const DevCtx& c, int32_t begin, int32_t end, int32_t* counter, int nsm, int reserve, cudaStream_t st);
+void launch_invert_diag(const DevCtx& c, cudaStream_t st);
 
 void launch_fwd_small(const DevCtx& c, int32_t begin, int32_t end, cudaStream_t st);
 void launch_bwd_small(const DevCtx& c, int32_t begin, int32_t end, cudaStream_t st);
-void launch_fwd_trsv(const DevCtx& c, int32_t begin, int32_t end, cudaStream_t st);
-void launch_fwd_gemv(const DevCtx& c, int32_t begin, int32_t end, cudaStream_t st);
-void launch_bwd_gemv(const DevCtx& c, int32_t begin, int32_t end, cudaStream_t st);
-void launch_bwd_trsv(const DevCtx& c, int32_t begin, int32_t end, cudaStream_t st);
+void launch_fwd_large(const DevCtx& c, int32_t begin, int32_t end, int nsm, cudaStream_t st);
+void launch_bwd_large(const DevCtx& c, int32_t begin, int32_t end, int nsm, cudaStream_t st);
 
 void launch_k1_rhs(const DevCtx& c, const DevMat& A, const double* d, const double* xi_p, const double* xi_d,
                    cudaStream_t st);
@@ -80,6 +90,7 @@ void launch_k2_rhs(const DevCtx& c, const DevMat& A, const double* xi_p, const d
 void launch_k2_recover(const DevCtx& c, const DevMat& A, double* dx, double* dy, cudaStream_t st);
 
 size_t small_factor_smem(int32_t max_elems, int32_t max_nrow);
-void kernels_static_init();   // cudaFuncSetAttribute calls
+cudaError_t kernels_static_init();   // cudaFuncSetAttribute calls
+cudaError_t factor_kernels_static_init();
 
 }  // namespace tlp

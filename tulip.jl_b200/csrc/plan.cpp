@@ -27,21 +27,21 @@ int64_t lx_position(const Symbolic& S, int32_t gi, int32_t gk) {
     return S.sn_xptr[t] + (int64_t)(gk - f) * nrow + pos;
 }
 
-static void emit_update_tiles(std::vector<UpdTask>& out, int32_t piece, int32_t kdim, int32_t kbeg, int32_t kend,
-                              int32_t nrow, int32_t tgt, int32_t diagflag) {
+// tiles of the update  C[rows >= k, cols kbeg..kend) -= L[rows, piece cols] S L[cols, piece cols]'
+static void emit_update_tiles(std::vector<UpdTask>& out, int32_t piece, int32_t kbeg, int32_t kend, int32_t nrow,
+                              int32_t tgt, int32_t TILE = tlp::TILE) {
     for (int32_t k0 = kbeg; k0 < kend; k0 += TILE) {
         const int32_t nk = std::min(TILE, kend - k0);
         for (int32_t i0 = k0; i0 < nrow; i0 += TILE) {
-            if (kdim == 0 && i0 != k0) break;   // nothing to subtract: only the diagonal tile (potrf) is needed
             UpdTask t;
             t.piece = piece;
-            t.kdim = kdim;
             t.i0 = i0;
             t.ni = std::min(TILE, nrow - i0);
             t.k0 = k0;
             t.nk = nk;
             t.tgt = tgt;
-            t.diag = (i0 == k0) ? diagflag : 0;
+            t.diag = (i0 == k0) ? 1 : 0;
+            t.pad = 0;
             out.push_back(t);
         }
     }
@@ -53,6 +53,9 @@ void build_plan(const Symbolic& S, const PlanOptions& opt, Plan& P) {
     P.pieces.clear();
     P.sn_small.assign(ns, 0);
     P.sn_level.assign(ns, 0);
+    P.sn_dblk.assign(ns, -1);
+    P.dblk_sn.clear();
+    P.dblk_idx.clear();
     P.seg_ptr.assign(ns + 1, 0);
     P.seg_k0.clear();
     P.seg_tgt.clear();
@@ -72,30 +75,30 @@ void build_plan(const Symbolic& S, const PlanOptions& opt, Plan& P) {
     }
 
     // items and levels
-    std::vector<int32_t> childmax(ns, -1);
-    std::vector<int32_t> first_piece(ns, -1), npieces(ns, 0);
+    std::vector<int32_t> childmax(ns, -1), base_level(ns, 0);
     int32_t maxlevel = -1;
     for (int32_t s = 0; s < ns; ++s) {
         const int32_t nc = sn_ncol(S, s), nr = sn_nrow(S, s);
         const int32_t base = childmax[s] + 1;
-        const bool small = ((int64_t)nc * nr <= opt.small_elems) && nc <= opt.small_ncol;
+        base_level[s] = base;
+        const bool small = ((int64_t)nc * nr <= opt.small_elems) && nc <= opt.small_ncol && nr <= opt.small_nrow;
         if (small) {
             P.sn_small[s] = 1;
             P.sn_level[s] = base;
             P.max_small_elems = std::max(P.max_small_elems, nc * nr);
             P.max_small_nrow = std::max(P.max_small_nrow, nr);
         } else {
-            const int32_t W = std::max(TILE, (opt.piece_width / TILE) * TILE);
-            const int32_t np = (nc + W - 1) / W;
-            first_piece[s] = (int32_t)P.pieces.size();
-            npieces[s] = np;
+            const int32_t np = (nc + PIECE - 1) / PIECE;
+            P.sn_dblk[s] = (int32_t)P.dblk_sn.size();
             for (int32_t k = 0; k < np; ++k) {
                 Piece pc;
                 pc.sn = s;
-                pc.c0 = S.sn_first[s] + k * W;
-                pc.c1 = std::min(S.sn_first[s + 1], pc.c0 + W);
+                pc.c0 = S.sn_first[s] + k * PIECE;
+                pc.c1 = std::min(S.sn_first[s + 1], pc.c0 + PIECE);
                 pc.level = base + k;
                 P.pieces.push_back(pc);
+                P.dblk_sn.push_back(s);
+                P.dblk_idx.push_back(k);
             }
             P.sn_level[s] = base + np - 1;
         }
@@ -103,20 +106,31 @@ void build_plan(const Symbolic& S, const PlanOptions& opt, Plan& P) {
         const int32_t par = S.sn_parent[s];
         if (par >= 0) childmax[par] = std::max(childmax[par], P.sn_level[s]);
     }
+    P.ndblk = (int32_t)P.dblk_sn.size();
     const int32_t nlev = maxlevel + 1;
     P.levels.assign(nlev, LevelPlan());
 
-    // group by level
-    std::vector<std::vector<int32_t>> lsmall(nlev), lpiece(nlev);
+    // level of the item (small supernode / column piece) every column belongs to
+    std::vector<int32_t> col_level(S.N, 0);
     for (int32_t s = 0; s < ns; ++s)
+        for (int32_t j = S.sn_first[s]; j < S.sn_first[s + 1]; ++j)
+            col_level[j] = P.sn_small[s] ? P.sn_level[s] : base_level[s] + (j - S.sn_first[s]) / PIECE;
+
+    std::vector<std::vector<int32_t>> lsmall(nlev), lpiece(nlev), llarge(nlev);
+    for (int32_t s = 0; s < ns; ++s) {
         if (P.sn_small[s]) lsmall[P.sn_level[s]].push_back(s);
+        else llarge[base_level[s]].push_back(s);
+    }
     for (int32_t p = 0; p < (int32_t)P.pieces.size(); ++p) lpiece[P.pieces[p].level].push_back(p);
 
     P.small_list.clear();
     P.level_pieces.clear();
     P.upd.clear();
+    P.upd128.clear();
     P.panel.clear();
-    P.solve.clear();
+    P.fwd_items.clear();
+    P.bwd_items.clear();
+    P.flops_update = P.flops_panel = 0.0;
     for (int32_t L = 0; L < nlev; ++L) {
         LevelPlan& lp = P.levels[L];
         lp.small_begin = (int32_t)P.small_list.size();
@@ -126,94 +140,107 @@ void build_plan(const Symbolic& S, const PlanOptions& opt, Plan& P) {
         P.level_pieces.insert(P.level_pieces.end(), lpiece[L].begin(), lpiece[L].end());
         lp.piece_end = (int32_t)P.level_pieces.size();
 
-        int32_t nsteps = 0;
-        for (int32_t p : lpiece[L]) nsteps = std::max(nsteps, (P.pieces[p].c1 - P.pieces[p].c0 + TILE - 1) / TILE);
-        lp.nsteps = nsteps;
-        lp.inner_begin.assign(nsteps, 0);
-        lp.inner_end.assign(nsteps, 0);
-        lp.panel_begin.assign(nsteps, 0);
-        lp.panel_end.assign(nsteps, 0);
-        for (int32_t t = 0; t < nsteps; ++t) {
-            lp.inner_begin[t] = (int32_t)P.upd.size();
-            for (int32_t p : lpiece[L]) {
-                const Piece& pc = P.pieces[p];
-                const int32_t w = pc.c1 - pc.c0;
-                if (t * TILE >= w) continue;
-                const int32_t f = S.sn_first[pc.sn];
-                const int32_t nrow = sn_nrow(S, pc.sn);
-                const int32_t kbeg = (pc.c0 - f) + t * TILE;
-                const int32_t kend = (pc.c0 - f) + std::min(w, (t + 1) * TILE);
-                // block column t of the piece: update with the piece's first t*TILE columns; the
-                // diagonal tile additionally factors itself (diag = 2)
-                emit_update_tiles(P.upd, p, t * TILE, kbeg, kend, nrow, pc.sn, 2);
+        // trsm row tiles below each piece's diagonal block
+        lp.panel_begin = (int32_t)P.panel.size();
+        for (int32_t p : lpiece[L]) {
+            const Piece& pc = P.pieces[p];
+            const int32_t f = S.sn_first[pc.sn];
+            const int32_t nrow = sn_nrow(S, pc.sn);
+            const int32_t w = pc.c1 - pc.c0;
+            for (int32_t r0 = pc.c1 - f; r0 < nrow; r0 += PIECE) {
+                PanelTask pt;
+                pt.piece = p;
+                pt.r0 = r0;
+                pt.nr = std::min(PIECE, nrow - r0);
+                pt.pad = 0;
+                P.panel.push_back(pt);
             }
-            lp.inner_end[t] = (int32_t)P.upd.size();
-            lp.panel_begin[t] = (int32_t)P.panel.size();
-            for (int32_t p : lpiece[L]) {
-                const Piece& pc = P.pieces[p];
-                const int32_t w = pc.c1 - pc.c0;
-                if (t * TILE >= w) continue;
-                const int32_t f = S.sn_first[pc.sn];
-                const int32_t nrow = sn_nrow(S, pc.sn);
-                const int32_t kend = (pc.c0 - f) + std::min(w, (t + 1) * TILE);
-                for (int32_t r0 = kend; r0 < nrow; r0 += 2 * TILE) {
-                    PanelTask pt;
-                    pt.piece = p;
-                    pt.step = t;
-                    pt.r0 = r0;
-                    pt.nr = std::min(2 * TILE, nrow - r0);
-                    P.panel.push_back(pt);
-                }
-            }
-            lp.panel_end[t] = (int32_t)P.panel.size();
+            P.flops_panel += (double)w * w * w / 3.0 + (double)(nrow - (pc.c1 - f)) * w * w;
         }
-        // external updates: rows below the piece (rest of own supernode, then ancestors)
+        lp.panel_end = (int32_t)P.panel.size();
+
+        // updates from each piece: rest of the own supernode, then ancestors
+        // Column blocks of <= 128 target columns (never straddling two targets).  A block whose first
+        // column belongs to an item of the next level is "urgent" (it gates that level's factorisation):
+        // 64x64 tiles on the main stream.  Everything else is "lazy": 128x128 tiles for the persistent
+        // side-stream kernel that runs underneath the critical chain.
         lp.ext_begin = (int32_t)P.upd.size();
+        lp.lazy_begin = (int32_t)P.upd128.size();
         for (int32_t p : lpiece[L]) {
             const Piece& pc = P.pieces[p];
             const int32_t s = pc.sn;
             const int32_t f = S.sn_first[s], l = S.sn_first[s + 1];
             const int32_t nrow = sn_nrow(S, s);
-            const int32_t w = pc.c1 - pc.c0;
-            if (pc.c1 < l) emit_update_tiles(P.upd, p, w, pc.c1 - f, l - f, nrow, s, 1);
+            const int32_t* rows = S.sn_rows.data() + S.sn_rowptr[s];
+            const size_t before = P.upd.size(), before128 = P.upd128.size();
+            auto emit_range = [&](int32_t kb, int32_t ke, int32_t tgt) {
+                for (int32_t k0 = kb; k0 < ke; k0 += TILE128) {
+                    const int32_t k1 = std::min(ke, k0 + TILE128);
+                    if (col_level[rows[k0]] <= L + 1) emit_update_tiles(P.upd, p, k0, k1, nrow, tgt, TILE);
+                    else emit_update_tiles(P.upd128, p, k0, k1, nrow, tgt, TILE);
+                }
+            };
+            if (pc.c1 < l) emit_range(pc.c1 - f, l - f, s);
             for (int64_t g = P.seg_ptr[s]; g < P.seg_ptr[s + 1]; ++g) {
                 const int32_t kb = P.seg_k0[g];
                 const int32_t ke = (g + 1 < P.seg_ptr[s + 1]) ? P.seg_k0[g + 1] : nrow;
-                emit_update_tiles(P.upd, p, w, kb, ke, nrow, P.seg_tgt[g], 1);
+                emit_range(kb, ke, P.seg_tgt[g]);
             }
+            const double w = pc.c1 - pc.c0;
+            auto tile_flops = [&](const UpdTask& t) {
+                double ent = (double)t.ni * t.nk;
+                if (t.diag) ent -= (double)t.nk * (t.nk - 1) / 2.0;
+                return 2.0 * ent * w;
+            };
+            for (size_t x = before; x < P.upd.size(); ++x) P.flops_update += tile_flops(P.upd[x]);
+            for (size_t x = before128; x < P.upd128.size(); ++x) P.flops_update += tile_flops(P.upd128[x]);
         }
         lp.ext_end = (int32_t)P.upd.size();
-        lp.ext_atomic = (lpiece[L].size() > 1) ? 1 : 0;
-        // solve tasks
-        lp.solve_begin = (int32_t)P.solve.size();
-        for (int32_t p : lpiece[L]) {
-            const Piece& pc = P.pieces[p];
-            const int32_t f = S.sn_first[pc.sn];
-            const int32_t nrow = sn_nrow(S, pc.sn);
-            for (int32_t r0 = pc.c1 - f; r0 < nrow; r0 += SOLVE_ROWS) {
-                SolveTask st;
-                st.piece = p;
-                st.r0 = r0;
-                st.nr = std::min(SOLVE_ROWS, nrow - r0);
-                P.solve.push_back(st);
+        lp.urgent_end = lp.ext_end;
+        lp.lazy_end = (int32_t)P.upd128.size();
+        lp.ext_atomic = 1;
+
+        // dense block-solve items of the supernodes that *start* at this level, in wavefront order
+        // (block index major) so that every dependency of an item precedes it in the list
+        lp.fwd_begin = (int32_t)P.fwd_items.size();
+        lp.bwd_begin = (int32_t)P.bwd_items.size();
+        {
+            int32_t maxblk = 0;
+            for (int32_t s : llarge[L]) {
+                const int32_t nc = sn_ncol(S, s), nr = sn_nrow(S, s);
+                maxblk = std::max(maxblk, (nc + SBLK - 1) / SBLK + (nr - nc + SBLK - 1) / SBLK);
             }
+            for (int32_t b = 0; b < maxblk; ++b)
+                for (int32_t s : llarge[L]) {
+                    const int32_t nc = sn_ncol(S, s), nr = sn_nrow(S, s);
+                    const int32_t ncb = (nc + SBLK - 1) / SBLK, nbb = (nr - nc + SBLK - 1) / SBLK;
+                    if (b >= ncb + nbb) continue;
+                    SolveItem it;
+                    it.sn = s;
+                    it.pad = 0;
+                    if (b < ncb) { it.kind = 0; it.blk = b; it.r0 = b * SBLK; it.nr = std::min(SBLK, nc - it.r0); }
+                    else { it.kind = 1; it.blk = b - ncb; it.r0 = nc + (b - ncb) * SBLK; it.nr = std::min(SBLK, nr - it.r0); }
+                    P.fwd_items.push_back(it);
+                }
+            int32_t maxcb = 0;
+            for (int32_t s : llarge[L]) maxcb = std::max(maxcb, (sn_ncol(S, s) + SBLK - 1) / SBLK);
+            for (int32_t d = 0; d < maxcb; ++d)      // d-th block from the end
+                for (int32_t s : llarge[L]) {
+                    const int32_t nc = sn_ncol(S, s);
+                    const int32_t ncb = (nc + SBLK - 1) / SBLK;
+                    if (d >= ncb) continue;
+                    SolveItem it;
+                    it.sn = s;
+                    it.pad = 0;
+                    it.kind = 0;
+                    it.blk = ncb - 1 - d;
+                    it.r0 = it.blk * SBLK;
+                    it.nr = std::min(SBLK, nc - it.r0);
+                    P.bwd_items.push_back(it);
+                }
         }
-        lp.solve_end = (int32_t)P.solve.size();
-    }
-    // algorithmic flops of the tile updates: 2*kdim per structurally needed output entry
-    auto tile_flops = [](const UpdTask& t) {
-        double ent = (double)t.ni * t.nk;
-        if (t.diag) ent -= (double)t.nk * (t.nk - 1) / 2.0;
-        return 2.0 * ent * (double)t.kdim;
-    };
-    P.flops_update_inner = P.flops_update_ext = 0.0;
-    for (const LevelPlan& lp : P.levels) {
-        for (int32_t t = 0; t < lp.nsteps; ++t)
-            for (int32_t x = lp.inner_begin[t]; x < lp.inner_end[t]; ++x) {
-                P.flops_update_inner += tile_flops(P.upd[x]);
-                if (P.upd[x].diag == 2) P.flops_update_inner += (double)P.upd[x].nk * P.upd[x].nk * P.upd[x].nk / 3.0;
-            }
-        for (int32_t x = lp.ext_begin; x < lp.ext_end; ++x) P.flops_update_ext += tile_flops(P.upd[x]);
+        lp.fwd_end = (int32_t)P.fwd_items.size();
+        lp.bwd_end = (int32_t)P.bwd_items.size();
     }
 }
 

@@ -10,52 +10,57 @@
 
 namespace tlp {
 
-constexpr int TILE = 64;          // update tile edge / panel inner block width
-constexpr int SOLVE_ROWS = 256;   // rows per CTA in the solve gemv kernels
+constexpr int TILE = 64;      // update tile edge (urgent tiles, main stream)
+constexpr int TILE128 = 128;  // update tile edge of the persistent side-stream kernel
+constexpr int PIECE = 128;    // column-piece width of wide supernodes = solve block size
+constexpr int SBLK = 128;     // block size of the dense triangular-solve kernels (== PIECE)
 
 struct PlanOptions {
-    int small_elems = 4096;   // supernodes with nrow*ncol <= small_elems (and ncol <= small_ncol) run in one CTA
-    int small_ncol = 32;
-    int piece_width = 256;    // wide supernodes are processed in column pieces of at most this width
+    int small_elems = 4096;   // supernodes with nrow*ncol <= small_elems, ncol <= small_ncol and
+    int small_ncol = 32;      // nrow <= small_nrow run in the one-CTA kernels
+    int small_nrow = 256;
 };
 
-// One column piece [c0,c1) of supernode sn (global permuted column indices).
+// One column piece [c0,c1) of supernode sn (global permuted column indices), c1-c0 <= PIECE.
 struct Piece {
     int32_t sn, c0, c1, level;
 };
 
-// C_tgt[pos(rows I), cols K] -= L_piece[I, 0:kdim] * S * L_piece[K, 0:kdim]'
+// C_tgt[pos(rows I), cols K] -= L_piece[I, :] * S * L_piece[K, :]'
 struct UpdTask {
-    int32_t piece;   // source piece
-    int32_t kdim;    // number of leading columns of the piece that take part
+    int32_t piece;   // source piece (all of its columns take part)
     int32_t i0, ni;  // I block: indices into the source supernode's row list
     int32_t k0, nk;  // K block: indices into the source supernode's row list (all rows map to columns of tgt)
     int32_t tgt;     // target supernode
-    int32_t diag;    // 1 = I and K blocks overlap (keep only row >= col)
+    int32_t diag;    // 1 = I and K blocks start at the same row (keep only row >= col)
+    int32_t pad;
 };
 
-// potrf of the diagonal block of inner step `step` of a piece + trsm of one row tile below it
+// triangular solve of one row tile (<= 128 rows) below a piece's factored diagonal block
 struct PanelTask {
-    int32_t piece, step;
-    int32_t r0, nr;   // row tile: indices into the supernode's row list (rows strictly below the diagonal block)
+    int32_t piece;
+    int32_t r0, nr;   // indices into the supernode's row list
+    int32_t pad;
 };
 
-// solve: one row tile of the rows below a piece (gemv / gemv-transposed)
-struct SolveTask {
-    int32_t piece;
-    int32_t r0, nr;
+// dense block solve work item: block `blk` of supernode sn; kind 0 = diagonal block (blk-th
+// 128-block of the columns), kind 1 = block of rows below the columns (forward sweep only)
+struct SolveItem {
+    int32_t sn, blk, kind;
+    int32_t r0, nr;   // row range of the block inside the supernode's row list
+    int32_t pad;
 };
 
 struct LevelPlan {
-    // ranges into the flat arrays of Plan
-    int32_t small_begin = 0, small_end = 0;        // Plan::small_list
-    int32_t piece_begin = 0, piece_end = 0;        // Plan::level_pieces
-    int32_t nsteps = 0;                            // max inner steps over this level's pieces
-    std::vector<int32_t> inner_begin, inner_end;   // [nsteps] ranges into Plan::upd (step 0 empty)
-    std::vector<int32_t> panel_begin, panel_end;   // [nsteps] ranges into Plan::panel
-    int32_t ext_begin = 0, ext_end = 0;            // external update tasks (Plan::upd)
+    int32_t small_begin = 0, small_end = 0;    // Plan::small_list
+    int32_t piece_begin = 0, piece_end = 0;    // Plan::level_pieces (diag-factor CTAs)
+    int32_t panel_begin = 0, panel_end = 0;    // Plan::panel (trsm row tiles)
+    int32_t ext_begin = 0, ext_end = 0;        // Plan::upd
+    int32_t urgent_end = 0;                    // == ext_end (all 64x64 tiles are urgent)
+    int32_t lazy_begin = 0, lazy_end = 0;      // Plan::upd128 (128x128 tiles, side stream)
     int32_t ext_atomic = 1;
-    int32_t solve_begin = 0, solve_end = 0;        // Plan::solve tasks of this level's pieces
+    int32_t fwd_begin = 0, fwd_end = 0;        // Plan::fwd_items (supernodes whose first piece is at this level)
+    int32_t bwd_begin = 0, bwd_end = 0;        // Plan::bwd_items
 };
 
 struct Plan {
@@ -63,6 +68,9 @@ struct Plan {
     std::vector<Piece> pieces;
     std::vector<int32_t> sn_small;        // [nsuper] 1 = handled by the one-CTA kernels
     std::vector<int32_t> sn_level;        // [nsuper] level of the supernode's last item
+    std::vector<int32_t> sn_dblk;         // [nsuper] index of the supernode's first diagonal block (-1 if small)
+    int32_t ndblk = 0;                    // total diagonal blocks of non-small supernodes
+    std::vector<int32_t> dblk_sn, dblk_idx;  // [ndblk] owner supernode / block index inside it
     // target segments of each supernode's below rows: consecutive below rows that are columns of the same target
     std::vector<int64_t> seg_ptr;         // [nsuper+1]
     std::vector<int32_t> seg_k0;          // first index (into the supernode's row list) of the segment
@@ -70,12 +78,14 @@ struct Plan {
     std::vector<int32_t> small_list;      // supernode ids grouped by level
     std::vector<int32_t> level_pieces;    // piece ids grouped by level
     std::vector<UpdTask> upd;
+    std::vector<UpdTask> upd128;
     std::vector<PanelTask> panel;
-    std::vector<SolveTask> solve;
+    std::vector<SolveItem> fwd_items, bwd_items;
     std::vector<LevelPlan> levels;
     int32_t max_small_elems = 0;          // largest nrow*ncol among small supernodes
     int32_t max_small_nrow = 0;
-    double flops_update_inner = 0.0, flops_update_ext = 0.0;   // algorithmic (lower-triangle) flops of the tile updates
+    double flops_update = 0.0;            // algorithmic (lower-triangle) flops of the tile updates
+    double flops_panel = 0.0;             // diag-block factor + trsm flops
 };
 
 void build_plan(const Symbolic& S, const PlanOptions& opt, Plan& P);

@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <climits>
 #include <cstdio>
 #include <cstring>
@@ -36,7 +38,8 @@ struct tlpb200_solver {
 
     bool on_device = false;
     int device = 0;
-    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t own_stream = nullptr, stream = nullptr, side_stream = nullptr;
+    std::vector<cudaEvent_t> ev_f, ev_lazy;   // per level: chain done / lazy update batch done
     std::vector<void*> allocs;
     size_t bytes_device = 0;
     DevCtx ctx{};
@@ -46,6 +49,9 @@ struct tlpb200_solver {
     double* h_pin = nullptr;   // pinned staging: 2n + m (update) / (n+m) in + (n+m) out (solve)
     int32_t* h_info = nullptr; // pinned
     size_t small_smem = 0;
+    int nsm = 148;
+    int32_t* lazy_ctr = nullptr;   // [2*nlevels] work-queue / exit counters of the lazy update launches
+    int chain_sms = 16;   // SMs kept free of the bulk-update work queue for the critical chain (TLPB200_CHAIN_SMS)
 
     cudaGraphExec_t g_update = nullptr, g_solve = nullptr;
     bool profiling = false;
@@ -121,8 +127,9 @@ struct Scope {
 
 void collect_profile(tlpb200_solver* s, bool reset_update_classes) {
     // called after a stream sync
-    const int lo = reset_update_classes ? 0 : 5, hi = reset_update_classes ? 5 : 12;
-    for (int c = lo; c < hi; ++c) { s->ms_class[c] = 0; s->n_class[c] = 0; }
+    static const bool is_update_class[16] = {1, 1, 1, 1, 1, 0, 0, 0, 1, 0, 1, 0, 0, 0, 0, 0};
+    for (int c = 0; c < 16; ++c)
+        if (is_update_class[c] == reset_update_classes) { s->ms_class[c] = 0; s->n_class[c] = 0; }
     for (size_t i = 0; i + 1 < s->pool_used; i += 2) {
         float ms = 0;
         cudaEventElapsedTime(&ms, s->pool[i], s->pool[i + 1]);
@@ -146,6 +153,7 @@ void enqueue_assemble(tlpb200_solver* s, int64_t& count) {
     Scope sc(s, 0);
     CK(cudaMemsetAsync(s->ctx.Lx, 0, (size_t)s->sym.lx_size * sizeof(double), st));
     CK(cudaMemsetAsync(s->ctx.info, 0x7f, sizeof(int32_t), st));
+    CK(cudaMemsetAsync(s->lazy_ctr, 0, (2 * s->plan.levels.size() + 2) * sizeof(int32_t), st));
     if (s->system == TLPB200_K1) {
         launch_compute_d(s->d_theta, s->d_regP, s->d_d, s->n, st);
         launch_assemble_k1(s->ctx, s->mat, s->d_d, s->d_regD, st);
@@ -156,20 +164,64 @@ void enqueue_assemble(tlpb200_solver* s, int64_t& count) {
     }
 }
 
+// Numeric factorisation.  Critical chain per level L on the main stream: one-CTA supernodes, diagonal
+// blocks, trsm, then the "urgent" update tiles (those that feed level L+1).  The bulk of the updates
+// ("lazy" tiles, needed from level L+2 on) runs on a lower-priority side stream underneath the chain.
+// Concurrent updates into the same ancestor entries are resolved by RED.ADD.F64, which is also the
+// faster epilogue on its own: 12.7 ms vs 17.7 ms per cfg2 factorisation for read-modify-write.
+// Profiling mode and TLPB200_NO_OVERLAP=1 use the single-stream order.
 void enqueue_factor(tlpb200_solver* s, int64_t& count) {
     cudaStream_t st = s->stream;
-    for (const LevelPlan& lp : s->plan.levels) {
+    static const bool no_overlap_env = getenv("TLPB200_NO_OVERLAP") != nullptr;
+    const bool overlap = !s->profiling && !no_overlap_env && s->side_stream != nullptr;
+    const auto& L = s->plan.levels;
+    const size_t nlev = L.size();
+    if (overlap && s->ev_f.size() < nlev) {
+        while (s->ev_f.size() < nlev) {
+            cudaEvent_t a, b;
+            CK(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+            s->ev_f.push_back(a);
+            s->ev_lazy.push_back(b);
+        }
+    }
+    std::vector<char> has_lazy(nlev, 0);
+    long last_lazy = -1;     // last level whose lazy batch was issued on the side stream
+    long waited = -1;        // last lazy level the main stream has waited for
+    for (size_t l = 0; l < nlev; ++l) {
+        const LevelPlan& lp = L[l];
+        if (overlap && l >= 2) {     // level l needs every lazy batch of levels <= l-2 (side stream is in-order)
+            long need = -1;
+            for (long q = (long)l - 2; q > waited; --q)
+                if (has_lazy[q]) { need = q; break; }
+            if (need > waited) { CK(cudaStreamWaitEvent(st, s->ev_lazy[need], 0)); waited = need; }
+        }
         if (lp.small_end > lp.small_begin) {
             Scope sc(s, 1);
             launch_small_factor(s->ctx, lp.small_begin, lp.small_end, s->small_smem, st);
             count++;
         }
-        for (int t = 0; t < lp.nsteps; ++t) {
-            if (lp.inner_end[t] > lp.inner_begin[t]) { Scope sc(s, 2); launch_update(s->ctx, lp.inner_begin[t], lp.inner_end[t], 0, st); count++; }
-            if (lp.panel_end[t] > lp.panel_begin[t]) { Scope sc(s, 3); launch_trsm(s->ctx, lp.panel_begin[t], lp.panel_end[t], st); count++; }
+        if (lp.piece_end > lp.piece_begin) { Scope sc(s, 2); launch_diag_factor(s->ctx, lp.piece_begin, lp.piece_end, st); count++; }
+        if (lp.panel_end > lp.panel_begin) { Scope sc(s, 3); launch_trsm(s->ctx, lp.panel_begin, lp.panel_end, st); count++; }
+        // the persistent bulk kernel leaves `chain_sms` SMs to the critical-chain kernels
+        if (lp.lazy_end > lp.lazy_begin) {
+            if (!overlap) {
+                Scope sc(s, 8);
+                launch_update_lazy(s->ctx, lp.lazy_begin, lp.lazy_end, s->lazy_ctr + 2 * l, s->nsm, 0, st);
+            } else {
+                CK(cudaEventRecord(s->ev_f[l], st));
+                CK(cudaStreamWaitEvent(s->side_stream, s->ev_f[l], 0));
+                launch_update_lazy(s->ctx, lp.lazy_begin, lp.lazy_end, s->lazy_ctr + 2 * l, s->nsm, s->chain_sms, s->side_stream);
+                CK(cudaEventRecord(s->ev_lazy[l], s->side_stream));
+                last_lazy = (long)l;
+                has_lazy[l] = 1;
+            }
+            count++;
         }
-        if (lp.ext_end > lp.ext_begin) { Scope sc(s, 4); launch_update(s->ctx, lp.ext_begin, lp.ext_end, lp.ext_atomic, st); count++; }
+        if (lp.ext_end > lp.ext_begin) { Scope sc(s, 4); launch_update(s->ctx, lp.ext_begin, lp.ext_end, 1, st); count++; }
     }
+    if (overlap && last_lazy > waited) CK(cudaStreamWaitEvent(st, s->ev_lazy[last_lazy], 0));   // join
+    if (s->ctx.ndblk > 0) { Scope sc(s, 10); launch_invert_diag(s->ctx, st); count++; }
     CK(cudaGetLastError());
 }
 
@@ -182,16 +234,15 @@ void enqueue_solve(tlpb200_solver* s, const double* xip, const double* xid, doub
     }
     count++;
     const auto& L = s->plan.levels;
+    if (s->ctx.ndblk > 0) CK(cudaMemsetAsync(s->ctx.flags, 0, (size_t)2 * s->ctx.ndblk * sizeof(int32_t), st));
     for (size_t l = 0; l < L.size(); ++l) {
         const LevelPlan& lp = L[l];
         if (lp.small_end > lp.small_begin) { Scope sc(s, 6); launch_fwd_small(s->ctx, lp.small_begin, lp.small_end, st); count++; }
-        if (lp.piece_end > lp.piece_begin) { Scope sc(s, 7); launch_fwd_trsv(s->ctx, lp.piece_begin, lp.piece_end, st); count++; }
-        if (lp.solve_end > lp.solve_begin) { Scope sc(s, 8); launch_fwd_gemv(s->ctx, lp.solve_begin, lp.solve_end, st); count++; }
+        if (lp.fwd_end > lp.fwd_begin) { Scope sc(s, 7); launch_fwd_large(s->ctx, lp.fwd_begin, lp.fwd_end, s->nsm, st); count++; }
     }
     for (size_t l = L.size(); l-- > 0;) {
         const LevelPlan& lp = L[l];
-        if (lp.solve_end > lp.solve_begin) { Scope sc(s, 9); launch_bwd_gemv(s->ctx, lp.solve_begin, lp.solve_end, st); count++; }
-        if (lp.piece_end > lp.piece_begin) { Scope sc(s, 10); launch_bwd_trsv(s->ctx, lp.piece_begin, lp.piece_end, st); count++; }
+        if (lp.bwd_end > lp.bwd_begin) { Scope sc(s, 9); launch_bwd_large(s->ctx, lp.bwd_begin, lp.bwd_end, s->nsm, st); count++; }
         if (lp.small_end > lp.small_begin) { Scope sc(s, 11); launch_bwd_small(s->ctx, lp.small_begin, lp.small_end, st); count++; }
     }
     {
@@ -337,9 +388,14 @@ void setup_device(tlpb200_solver* s) {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, s->device));
     if (prop.major != 10) throw std::runtime_error("tlpb200 is built for sm_100a (B200) only; found compute capability " + std::to_string(prop.major) + "." + std::to_string(prop.minor));
-    CK(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
+    {
+        int lo = 0, hi = 0;   // numerically lower = higher priority
+        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CK(cudaStreamCreateWithPriority(&s->own_stream, cudaStreamNonBlocking, hi));
+        CK(cudaStreamCreateWithPriority(&s->side_stream, cudaStreamNonBlocking, lo));
+    }
     s->stream = s->own_stream;
-    kernels_static_init();
+    CK(kernels_static_init());
     for (auto& ev : s->ev) CK(cudaEventCreate(&ev));
 
     const Symbolic& S = s->sym;
@@ -362,14 +418,25 @@ void setup_device(tlpb200_solver* s) {
     c.small_list = upload(s, P.small_list);
     c.level_pieces = upload(s, P.level_pieces);
     c.upd = upload(s, P.upd);
+    c.upd_lazy = upload(s, P.upd128);
+    s->lazy_ctr = dalloc<int32_t>(s, 2 * P.levels.size() + 2);
     c.panel = upload(s, P.panel);
-    c.solve = upload(s, P.solve);
+    c.fwd_items = upload(s, P.fwd_items);
+    c.bwd_items = upload(s, P.bwd_items);
+    c.sn_dblk = upload(s, P.sn_dblk);
+    c.dblk_sn = upload(s, P.dblk_sn);
+    c.dblk_idx = upload(s, P.dblk_idx);
+    c.ndblk = P.ndblk;
+    c.has_neg = (s->system == TLPB200_K2) ? 1 : 0;
     c.Lx = dalloc<double>(s, (size_t)S.lx_size);
+    c.Dinv = dalloc<double>(s, (size_t)P.ndblk * SBLK * SBLK);
+    c.DinvT = dalloc<double>(s, (size_t)P.ndblk * SBLK * SBLK);
+    c.flags = dalloc<int32_t>(s, (size_t)2 * P.ndblk);
     c.info = dalloc<int32_t>(s, 4);
     c.wk = dalloc<double>(s, (size_t)S.N);
-    c.acc = dalloc<double>(s, (size_t)S.N);
-    CK(cudaMemset(c.acc, 0, std::max<size_t>(S.N, 1) * sizeof(double)));
     CK(cudaMemset(c.wk, 0, std::max<size_t>(S.N, 1) * sizeof(double)));
+    s->nsm = prop.multiProcessorCount;
+    if (const char* e = getenv("TLPB200_CHAIN_SMS")) s->chain_sms = std::max(0, std::min(s->nsm - 1, atoi(e)));
 
     DevMat& A = s->mat;
     A.m = s->m; A.n = s->n; A.nnz = s->nnz;
@@ -441,7 +508,7 @@ int tlpb200_create(tlpb200_solver** out, int64_t m, int64_t n, const int64_t* co
         return fail(s, TLPB200_BAD_ARG, "tlpb200_create: bad argument");
     if ((system == TLPB200_K1 ? m : m + n) > (int64_t)INT32_MAX - 1)
         return fail(s, TLPB200_BAD_ARG, "tlpb200_create: system order exceeds 32-bit indexing");
-    if (s->opt.piece_width < 64 || s->opt.piece_width > 128) s->opt.piece_width = 128;
+    s->opt.piece_width = PIECE;
     if (s->opt.small_elems < 64) s->opt.small_elems = 4096;
     if (s->opt.small_elems > 8192) s->opt.small_elems = 8192;
     s->system = system;
@@ -465,7 +532,6 @@ int tlpb200_create(tlpb200_solver** out, int64_t m, int64_t n, const int64_t* co
             analyze_pattern(P, so, sg.data(), s->sym);
         }
         PlanOptions po;
-        po.piece_width = s->opt.piece_width;
         po.small_elems = s->opt.small_elems;
         build_plan(s->sym, po, s->plan);
         if (system == TLPB200_K1)
@@ -494,16 +560,24 @@ int tlpb200_update(tlpb200_solver* s, const double* theta_inv, const double* reg
     REQUIRE_DEVICE(s);
     if (!theta_inv || !regP || !regD) return fail(s, TLPB200_BAD_ARG, "tlpb200_update: null vector");
     try {
+        static const bool trace = getenv("TLPB200_TRACE") != nullptr;
+        auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        const double t0 = trace ? now() : 0;
         CK(cudaSetDevice(s->device));
         const size_t n = (size_t)s->n, m = (size_t)s->m;
         std::memcpy(s->h_pin, theta_inv, n * 8);
         std::memcpy(s->h_pin + n, regP, n * 8);
         std::memcpy(s->h_pin + 2 * n, regD, m * 8);
+        const double t1 = trace ? now() : 0;
         CK(cudaMemcpyAsync(s->d_theta, s->h_pin, n * 8, cudaMemcpyHostToDevice, s->stream));
         CK(cudaMemcpyAsync(s->d_regP, s->h_pin + n, n * 8, cudaMemcpyHostToDevice, s->stream));
         CK(cudaMemcpyAsync(s->d_regD, s->h_pin + 2 * n, m * 8, cudaMemcpyHostToDevice, s->stream));
+        const double t2 = trace ? now() : 0;
         run_update(s);
-        return finish_update(s, bad_pivot);
+        const double t3 = trace ? now() : 0;
+        const int rc = finish_update(s, bad_pivot);
+        if (trace) fprintf(stderr, "[tlpb200 trace] update: stage %.3f  h2d-enqueue %.3f  launch %.3f  sync %.3f ms\n", t1 - t0, t2 - t1, t3 - t2, now() - t3);
+        return rc;
     } catch (const CudaFail& f) {
         return cuda_fail(s, f);
     }
@@ -631,8 +705,8 @@ int tlpb200_stats_get(const tlpb200_solver* s, tlpb200_stats* o) {
     o->n_update = s->n_update;
     o->n_solve = s->n_solve;
     o->bytes_device = (int64_t)s->bytes_device;
-    o->flops_update_inner = s->plan.flops_update_inner;
-    o->flops_update_ext = s->plan.flops_update_ext;
+    o->flops_update_inner = s->plan.flops_panel;
+    o->flops_update_ext = s->plan.flops_update;
     for (int c = 0; c < 16; ++c) { o->ms_class[c] = s->ms_class[c]; o->n_class[c] = s->n_class[c]; }
     return TLPB200_OK;
 }
@@ -702,6 +776,9 @@ void tlpb200_destroy(tlpb200_solver* s) {
         if (s->h_info) cudaFreeHost(s->h_info);
         for (auto& ev : s->ev) if (ev) cudaEventDestroy(ev);
         for (auto& ev : s->pool) cudaEventDestroy(ev);
+        for (auto& ev : s->ev_f) cudaEventDestroy(ev);
+        for (auto& ev : s->ev_lazy) cudaEventDestroy(ev);
+        if (s->side_stream) cudaStreamDestroy(s->side_stream);
         if (s->own_stream) cudaStreamDestroy(s->own_stream);
     }
     delete s;

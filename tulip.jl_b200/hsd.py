@@ -37,6 +37,7 @@ class IPMOptions:                      # src/IPM/options.jl:1-25
     CentralityOutlierThreshold: float = 0.1
     PRegMin: float = _SQRT_EPS
     DRegMin: float = _SQRT_EPS
+    Threads: int = 1                   # src/parameters.jl:7 -- model.jl:73 BLAS.set_num_threads(params.Threads)
 
 
 class _Dir:
@@ -126,6 +127,19 @@ class HSD:
 
     # HSD.jl:203-350
     def optimize(self, max_iter=None, callback=None):
+        # model.jl:73: BLAS.set_num_threads(params.Threads) (default 1).  Besides mirroring the reference this
+        # matters on the GPU box: a multi-threaded ddot leaves 100+ OpenBLAS workers spinning, which starves the
+        # CUDA driver threads and more than doubles the wall time of the next update! (measured).
+        try:
+            from threadpoolctl import threadpool_limits
+            ctx = threadpool_limits(limits=max(1, int(self.params.Threads)), user_api="blas")
+        except Exception:          # pragma: no cover
+            import contextlib
+            ctx = contextlib.nullcontext()
+        with ctx:
+            return self._optimize(max_iter, callback)
+
+    def _optimize(self, max_iter=None, callback=None):
         P = self.params
         tstart = time.time()
         self.niter = 0
