@@ -49,7 +49,8 @@ typedef struct tlpb200_options {
     int32_t relax_always;  /* amalgamation: always merge when merged width <= this (default 8) */
     int32_t use_graph;     /* 1 = replay update!/solve! as CUDA graphs (default 1) */
     int32_t analyze_only;  /* 1 = host symbolic analysis only, no device is touched (tests, no GPU) */
-    int32_t reserved[9];
+    int32_t rank, nranks;  /* multi-GPU subtree sharding: this process's rank and the world size (default 0, 1) */
+    int32_t reserved[7];
 } tlpb200_options;
 
 typedef struct tlpb200_stats {
@@ -120,6 +121,21 @@ int tlpb200_get_structure(const tlpb200_solver* s, int64_t* rowptr, int32_t* row
  * tlpb200_debug_assemble call, the assembled matrix) back to the host: Lx[nnzL_stored]. */
 int tlpb200_debug_assemble(tlpb200_solver* s, const double* theta_inv, const double* regP, const double* regD);
 int tlpb200_debug_get_lx(tlpb200_solver* s, double* lx, int64_t* xptr /* nsuper+1, may be NULL */);
+
+/* ---- multi-GPU, one process per GPU (no counterpart in the reference, NEWS.md:31) -------------
+ * Created with opt.nranks > 1 every rank analyses the same matrix, owns the elimination-tree subtrees
+ * assigned to it (owner[s] == rank) and replicates the top part (owner[s] == -1).  The caller performs the
+ * collectives on the exposed device buffers between the phases (tulip.jl_b200/parallel.py uses NCCL):
+ *   update_begin -> all_reduce(sum, top_panels) -> update_end (+ all_reduce(max) of the return codes)
+ *   solve_begin  -> all_reduce(sum, work_vector) -> solve_mid -> all_reduce(sum, work_vector) -> solve_end */
+int tlpb200_dist_info(const tlpb200_solver* s, int32_t* owner /* nsuper */, int64_t* top_offset, int64_t* top_count);
+int tlpb200_update_begin(tlpb200_solver* s, const double* theta_inv, const double* regP, const double* regD);
+int tlpb200_top_panels(tlpb200_solver* s, void** dptr, int64_t* count);
+int tlpb200_update_end(tlpb200_solver* s, int64_t* bad_pivot);
+int tlpb200_solve_begin(tlpb200_solver* s, const double* xi_p, const double* xi_d);
+int tlpb200_work_vector(tlpb200_solver* s, void** dptr, int64_t* count);
+int tlpb200_solve_mid(tlpb200_solver* s);
+int tlpb200_solve_end(tlpb200_solver* s, double* dx, double* dy);
 
 const char* tlpb200_last_error(const tlpb200_solver* s);
 const char* tlpb200_backend_name(void);            /* KKT.backend(kkt)       (KKT.jl:114) */

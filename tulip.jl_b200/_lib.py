@@ -20,7 +20,8 @@ K1, K2 = 1, 2
 class Options(C.Structure):
     _fields_ = [("ordering", C.c_int32), ("device", C.c_int32), ("piece_width", C.c_int32),
                 ("small_elems", C.c_int32), ("relax_always", C.c_int32), ("use_graph", C.c_int32),
-                ("analyze_only", C.c_int32), ("reserved", C.c_int32 * 9)]
+                ("analyze_only", C.c_int32), ("rank", C.c_int32), ("nranks", C.c_int32),
+                ("reserved", C.c_int32 * 7)]
 
 
 class Stats(C.Structure):
@@ -55,6 +56,8 @@ SYMBOLS = [
     "tlpb200_synchronize", "tlpb200_set_profiling", "tlpb200_stats_get", "tlpb200_get_symbolic",
     "tlpb200_get_structure", "tlpb200_debug_assemble", "tlpb200_debug_get_lx", "tlpb200_last_error",
     "tlpb200_backend_name", "tlpb200_linear_system", "tlpb200_destroy",
+    "tlpb200_dist_info", "tlpb200_update_begin", "tlpb200_top_panels", "tlpb200_update_end",
+    "tlpb200_solve_begin", "tlpb200_work_vector", "tlpb200_solve_mid", "tlpb200_solve_end",
 ]
 
 _lib = None
@@ -89,6 +92,17 @@ def load():
     lib.tlpb200_get_structure.argtypes = [p, p, p]
     lib.tlpb200_debug_assemble.argtypes = [p, dp, dp, dp]
     lib.tlpb200_debug_get_lx.argtypes = [p, dp, C.POINTER(C.c_int64)]
+    lib.tlpb200_dist_info.argtypes = [p, p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.tlpb200_update_begin.argtypes = [p, dp, dp, dp]
+    lib.tlpb200_top_panels.argtypes = [p, C.POINTER(p), C.POINTER(C.c_int64)]
+    lib.tlpb200_update_end.argtypes = [p, C.POINTER(C.c_int64)]
+    lib.tlpb200_solve_begin.argtypes = [p, dp, dp]
+    lib.tlpb200_work_vector.argtypes = [p, C.POINTER(p), C.POINTER(C.c_int64)]
+    lib.tlpb200_solve_mid.argtypes = [p]
+    lib.tlpb200_solve_end.argtypes = [p, dp, dp]
+    for name in ("tlpb200_dist_info", "tlpb200_update_begin", "tlpb200_top_panels", "tlpb200_update_end",
+                 "tlpb200_solve_begin", "tlpb200_work_vector", "tlpb200_solve_mid", "tlpb200_solve_end"):
+        getattr(lib, name).restype = C.c_int
     lib.tlpb200_last_error.argtypes = [p]
     lib.tlpb200_last_error.restype = C.c_char_p
     lib.tlpb200_backend_name.argtypes = []

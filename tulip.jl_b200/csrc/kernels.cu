@@ -106,6 +106,7 @@ constexpr int SMALL_THREADS = 128;
 __global__ void __launch_bounds__(SMALL_THREADS) k_small_factor(DevCtx c, int32_t begin) {
     extern __shared__ double smem_d[];
     const int32_t s = c.small_list[begin + blockIdx.x];
+    if (c.skip && c.skip[s]) return;
     const int32_t f = c.sn_first[s];
     const int32_t nc = c.sn_first[s + 1] - f;
     const int64_t rp = c.sn_rowptr[s];
@@ -179,6 +180,7 @@ __global__ void __launch_bounds__(INV_THREADS) k_invert_diag(DevCtx c) {
     const int LDI = SBLK + 1;
     const int32_t b = blockIdx.x;
     const int32_t s = c.dblk_sn[b], bi = c.dblk_idx[b];
+    if (c.skip && c.skip[s]) return;
     const int32_t f = c.sn_first[s];
     const int32_t nc = c.sn_first[s + 1] - f;
     const int32_t ld = (int32_t)(c.sn_rowptr[s + 1] - c.sn_rowptr[s]);
@@ -225,6 +227,7 @@ __global__ void __launch_bounds__(32 * SOLVE_SMALL_WARPS) k_fwd_small(DevCtx c, 
     const int32_t idx = begin + blockIdx.x * SOLVE_SMALL_WARPS + (threadIdx.x >> 5);
     if (idx >= end) return;
     const int32_t s = c.small_list[idx];
+    if (c.skip && c.skip[s]) return;
     const int32_t f = c.sn_first[s];
     const int32_t nc = c.sn_first[s + 1] - f;
     const int64_t rp = c.sn_rowptr[s];
@@ -254,6 +257,7 @@ __global__ void __launch_bounds__(32 * SOLVE_SMALL_WARPS) k_bwd_small(DevCtx c, 
     const int32_t idx = begin + blockIdx.x * SOLVE_SMALL_WARPS + (threadIdx.x >> 5);
     if (idx >= end) return;
     const int32_t s = c.small_list[idx];
+    if (c.skip && c.skip[s]) return;
     const int32_t f = c.sn_first[s];
     const int32_t nc = c.sn_first[s + 1] - f;
     const int64_t rp = c.sn_rowptr[s];
@@ -302,6 +306,7 @@ __global__ void __launch_bounds__(SL_THREADS, 1) k_fwd_large(DevCtx c, int32_t b
     for (int32_t it = begin + blockIdx.x; it < end; it += gridDim.x) {
         const SolveItem I = c.fwd_items[it];
         const int32_t s = I.sn;
+        if (c.skip && c.skip[s]) continue;
         const int32_t f = c.sn_first[s];
         const int32_t nc = c.sn_first[s + 1] - f;
         const int64_t rp = c.sn_rowptr[s];
@@ -373,6 +378,7 @@ __global__ void __launch_bounds__(SL_THREADS, 1) k_bwd_large(DevCtx c, int32_t b
     for (int32_t it = begin + blockIdx.x; it < end; it += gridDim.x) {
         const SolveItem I = c.bwd_items[it];
         const int32_t s = I.sn;
+        if (c.skip && c.skip[s]) continue;
         const int32_t f = c.sn_first[s];
         const int32_t nc = c.sn_first[s + 1] - f;
         const int64_t rp = c.sn_rowptr[s];
@@ -487,6 +493,11 @@ __global__ void k_k2_recover(DevCtx c, DevMat A, double* __restrict__ dx, double
     if (v < A.n) dx[v] = x; else dy[v - A.n] = x;
 }
 
+__global__ void k_zero_unowned(DevCtx c, const int8_t* __restrict__ keep) {
+    const int32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < c.N && !keep[q]) c.wk[q] = 0.0;
+}
+
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
@@ -546,6 +557,9 @@ void launch_fwd_large(const DevCtx& c, int32_t begin, int32_t end, int nsm, cuda
 }
 void launch_bwd_large(const DevCtx& c, int32_t begin, int32_t end, int nsm, cudaStream_t st) {
     if (end > begin) k_bwd_large<<<min(end - begin, nsm), SL_THREADS, SL_SMEM, st>>>(c, begin, end);
+}
+void launch_zero_unowned(const DevCtx& c, const int8_t* keep, cudaStream_t st) {
+    if (c.N > 0) k_zero_unowned<<<nblk(c.N, 256), 256, 0, st>>>(c, keep);
 }
 void launch_k1_rhs(const DevCtx& c, const DevMat& A, const double* d, const double* xi_p, const double* xi_d,
                    cudaStream_t st) {

@@ -44,6 +44,7 @@ struct DevCtx {
     int32_t N;
     int32_t ndblk;
     int32_t has_neg;   // 1 when some pivots are expected negative (K2)
+    const int8_t* skip;   // multi-GPU: skip[s] != 0 -> supernode s is not processed in this phase on this rank (nullptr: none)
 };
 
 // matrix A on the device (CSC + CSR copies) and the assemble maps
@@ -82,6 +83,7 @@ void launch_bwd_small(const DevCtx& c, int32_t begin, int32_t end, cudaStream_t 
 void launch_fwd_large(const DevCtx& c, int32_t begin, int32_t end, int nsm, cudaStream_t st);
 void launch_bwd_large(const DevCtx& c, int32_t begin, int32_t end, int nsm, cudaStream_t st);
 
+void launch_zero_unowned(const DevCtx& c, const int8_t* keep, cudaStream_t st);   // wk[q] = 0 where keep[q] == 0
 void launch_k1_rhs(const DevCtx& c, const DevMat& A, const double* d, const double* xi_p, const double* xi_d,
                    cudaStream_t st);
 void launch_k1_recover(const DevCtx& c, const DevMat& A, const double* d, const double* xi_d, double* dx, double* dy,

@@ -94,6 +94,7 @@ __global__ void __launch_bounds__(DF_THREADS, 1) k_diag_factor(DevCtx c, int32_t
     double* Wp = Wd + NBD * LDW;         // [PIECE][LDW]  u_kj / d_j of the current block, rows below it
     const Piece pc = c.pieces[c.level_pieces[begin + blockIdx.x]];
     const int32_t s = pc.sn;
+    if (c.skip && c.skip[s]) return;
     const int32_t f = c.sn_first[s];
     const int32_t ld = (int32_t)(c.sn_rowptr[s + 1] - c.sn_rowptr[s]);
     const int32_t lc0 = pc.c0 - f, w = pc.c1 - pc.c0;
@@ -228,6 +229,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_trsm(DevCtx c, int32_t begin)
     const PanelTask T = c.panel[begin + blockIdx.x];
     const Piece pc = c.pieces[T.piece];
     const int32_t s = pc.sn;
+    if (c.skip && c.skip[s]) return;
     const int32_t f = c.sn_first[s];
     const int32_t ld = (int32_t)(c.sn_rowptr[s + 1] - c.sn_rowptr[s]);
     const int32_t kb = pc.c0 - f, w = pc.c1 - pc.c0;
@@ -326,6 +328,7 @@ struct UpdShared {
 __device__ __forceinline__ void update_tile(const DevCtx& c, const UpdTask& T, double* smem_d, UpdShared& sh, int atomic) {
     const Piece pc = c.pieces[T.piece];
     const int32_t s = pc.sn;
+    if (c.skip && c.skip[s]) return;     // uniform per CTA
     const int32_t f = c.sn_first[s];
     const int64_t rp = c.sn_rowptr[s];
     const int32_t ld = (int32_t)(c.sn_rowptr[s + 1] - rp);

@@ -322,3 +322,92 @@ void build_assembly_k2(const Symbolic& S, int64_t m, int64_t n, const int64_t* c
 }
 
 }  // namespace tlp
+
+// ------------------------------------------------------------------------------------------
+// Multi-GPU: shard independent elimination-tree subtrees across ranks.  Every rank runs
+// this on the same symbolic analysis and gets the same answer.  owner[s] = rank that factors
+// supernode s, or -1 for the replicated top part (the separator: ancestors of the cut).
+// ------------------------------------------------------------------------------------------
+namespace tlp {
+
+void partition_subtrees(const Symbolic& S, int nranks, std::vector<int32_t>& owner, std::vector<double>* rank_work) {
+    const int32_t ns = S.nsuper;
+    owner.assign(ns, 0);
+    if (rank_work) rank_work->assign(std::max(nranks, 1), 0.0);
+    if (nranks <= 1 || ns == 0) return;
+    // work of a supernode ~ sum of squared column counts of its columns; subtree sums bottom-up
+    std::vector<double> work(ns, 0.0), sub(ns, 0.0);
+    for (int32_t s = 0; s < ns; ++s) {
+        for (int32_t j = S.sn_first[s]; j < S.sn_first[s + 1]; ++j) work[s] += (double)S.colcount[j] * S.colcount[j];
+        sub[s] += work[s];
+        if (S.sn_parent[s] >= 0) sub[S.sn_parent[s]] += sub[s];
+    }
+    std::vector<std::vector<int32_t>> kids(ns);
+    std::vector<int32_t> cand;                  // current subtree roots
+    for (int32_t s = 0; s < ns; ++s) {
+        if (S.sn_parent[s] >= 0) kids[S.sn_parent[s]].push_back(s);
+        else cand.push_back(s);
+    }
+    std::vector<char> top(ns, 0);
+    for (;;) {
+        // heaviest candidate (ties: lowest index)
+        int32_t best = -1;
+        double total = 0.0;
+        for (int32_t r : cand) {
+            total += sub[r];
+            if (best < 0 || sub[r] > sub[best]) best = r;
+        }
+        if (best < 0) break;
+        const bool enough = (int)cand.size() >= 2 * nranks && sub[best] <= 0.6 * total / nranks;
+        if (enough || kids[best].empty()) break;
+        top[best] = 1;
+        cand.erase(std::find(cand.begin(), cand.end(), best));
+        for (int32_t k : kids[best]) cand.push_back(k);
+    }
+    // longest-processing-time assignment of the subtrees
+    std::vector<int32_t> order(cand);
+    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return sub[a] != sub[b] ? sub[a] > sub[b] : a < b; });
+    std::vector<double> load(nranks, 0.0);
+    std::vector<int32_t> root_owner(ns, -1);
+    for (int32_t r : order) {
+        int g = 0;
+        for (int q = 1; q < nranks; ++q) if (load[q] < load[g]) g = q;
+        root_owner[r] = g;
+        load[g] += sub[r];
+    }
+    // propagate down: supernodes are postordered, so parents come after children -> walk top-down
+    for (int32_t s = ns - 1; s >= 0; --s) {
+        if (top[s]) owner[s] = -1;
+        else if (root_owner[s] >= 0) owner[s] = root_owner[s];
+        else owner[s] = owner[S.sn_parent[s]];
+    }
+    if (rank_work) *rank_work = load;
+}
+
+// Panel storage order: supernodes of the subtrees first, the replicated top part last (so that the
+// top panels form one contiguous range for the all-reduce).  Recomputes sn_xptr and diagpos.
+int64_t relayout_panels(Symbolic& S, const std::vector<int32_t>& owner) {
+    const int32_t ns = S.nsuper;
+    int64_t off = 0, top_begin = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+        if (pass == 1) top_begin = off;
+        for (int32_t s = 0; s < ns; ++s) {
+            if ((owner[s] < 0) != (pass == 1)) continue;
+            const int64_t ncol = S.sn_first[s + 1] - S.sn_first[s];
+            const int64_t nrow = S.sn_rowptr[s + 1] - S.sn_rowptr[s];
+            S.sn_xptr[s] = off;
+            off += nrow * ncol;
+        }
+    }
+    S.sn_xptr[ns] = off;     // == lx_size (the last entry is no longer "end of supernode ns-1")
+    for (int32_t s = 0; s < ns; ++s) {
+        const int64_t nrow = S.sn_rowptr[s + 1] - S.sn_rowptr[s];
+        for (int32_t j = S.sn_first[s]; j < S.sn_first[s + 1]; ++j) {
+            const int64_t lc = j - S.sn_first[s];
+            S.diagpos[j] = S.sn_xptr[s] + lc * nrow + lc;
+        }
+    }
+    return top_begin;
+}
+
+}  // namespace tlp

@@ -43,6 +43,12 @@ struct tlpb200_solver {
     std::vector<void*> allocs;
     size_t bytes_device = 0;
     DevCtx ctx{};
+    DevCtx ctxA{}, ctxB{};        // multi-GPU phases: own subtrees / replicated top part
+    const DevCtx* cur = nullptr;  // context the enqueue_* helpers launch with
+    int rank = 0, nranks = 1;
+    std::vector<int32_t> owner;   // [nsuper] rank owning each supernode, -1 = replicated top part
+    int64_t top_begin = 0;        // offset of the top panels inside Lx
+    int8_t* d_keep = nullptr;     // [N] 1 = this rank contributes wk[q] to the all-reduce
     DevMat mat{};
     double *d_theta = nullptr, *d_regP = nullptr, *d_regD = nullptr, *d_d = nullptr;
     double *d_xip = nullptr, *d_xid = nullptr, *d_dx = nullptr, *d_dy = nullptr;
@@ -198,60 +204,80 @@ void enqueue_factor(tlpb200_solver* s, int64_t& count) {
         }
         if (lp.small_end > lp.small_begin) {
             Scope sc(s, 1);
-            launch_small_factor(s->ctx, lp.small_begin, lp.small_end, s->small_smem, st);
+            launch_small_factor((*s->cur), lp.small_begin, lp.small_end, s->small_smem, st);
             count++;
         }
-        if (lp.piece_end > lp.piece_begin) { Scope sc(s, 2); launch_diag_factor(s->ctx, lp.piece_begin, lp.piece_end, st); count++; }
-        if (lp.panel_end > lp.panel_begin) { Scope sc(s, 3); launch_trsm(s->ctx, lp.panel_begin, lp.panel_end, st); count++; }
+        if (lp.piece_end > lp.piece_begin) { Scope sc(s, 2); launch_diag_factor((*s->cur), lp.piece_begin, lp.piece_end, st); count++; }
+        if (lp.panel_end > lp.panel_begin) { Scope sc(s, 3); launch_trsm((*s->cur), lp.panel_begin, lp.panel_end, st); count++; }
         // the persistent bulk kernel leaves `chain_sms` SMs to the critical-chain kernels
         if (lp.lazy_end > lp.lazy_begin) {
             if (!overlap) {
                 Scope sc(s, 8);
-                launch_update_lazy(s->ctx, lp.lazy_begin, lp.lazy_end, s->lazy_ctr + 2 * l, s->nsm, 0, st);
+                launch_update_lazy((*s->cur), lp.lazy_begin, lp.lazy_end, s->lazy_ctr + 2 * l, s->nsm, 0, st);
             } else {
                 CK(cudaEventRecord(s->ev_f[l], st));
                 CK(cudaStreamWaitEvent(s->side_stream, s->ev_f[l], 0));
-                launch_update_lazy(s->ctx, lp.lazy_begin, lp.lazy_end, s->lazy_ctr + 2 * l, s->nsm, s->chain_sms, s->side_stream);
+                launch_update_lazy((*s->cur), lp.lazy_begin, lp.lazy_end, s->lazy_ctr + 2 * l, s->nsm, s->chain_sms, s->side_stream);
                 CK(cudaEventRecord(s->ev_lazy[l], s->side_stream));
                 last_lazy = (long)l;
                 has_lazy[l] = 1;
             }
             count++;
         }
-        if (lp.ext_end > lp.ext_begin) { Scope sc(s, 4); launch_update(s->ctx, lp.ext_begin, lp.ext_end, 1, st); count++; }
+        if (lp.ext_end > lp.ext_begin) { Scope sc(s, 4); launch_update((*s->cur), lp.ext_begin, lp.ext_end, 1, st); count++; }
     }
     if (overlap && last_lazy > waited) CK(cudaStreamWaitEvent(st, s->ev_lazy[last_lazy], 0));   // join
-    if (s->ctx.ndblk > 0) { Scope sc(s, 10); launch_invert_diag(s->ctx, st); count++; }
+    if ((*s->cur).ndblk > 0) { Scope sc(s, 10); launch_invert_diag((*s->cur), st); count++; }
+    CK(cudaGetLastError());
+}
+
+void enqueue_rhs(tlpb200_solver* s, const double* xip, const double* xid, int64_t& count) {
+    cudaStream_t st = s->stream;
+    {
+        Scope sc(s, 5);
+        if (s->system == TLPB200_K1) launch_k1_rhs((*s->cur), s->mat, s->d_d, xip, xid, st);
+        else launch_k2_rhs((*s->cur), s->mat, xip, xid, st);
+    }
+    count++;
+    if ((*s->cur).ndblk > 0) CK(cudaMemsetAsync((*s->cur).flags, 0, (size_t)2 * (*s->cur).ndblk * sizeof(int32_t), st));
+}
+
+void enqueue_fwd(tlpb200_solver* s, int64_t& count) {
+    cudaStream_t st = s->stream;
+    const auto& L = s->plan.levels;
+    for (size_t l = 0; l < L.size(); ++l) {
+        const LevelPlan& lp = L[l];
+        if (lp.small_end > lp.small_begin) { Scope sc(s, 6); launch_fwd_small((*s->cur), lp.small_begin, lp.small_end, st); count++; }
+        if (lp.fwd_end > lp.fwd_begin) { Scope sc(s, 7); launch_fwd_large((*s->cur), lp.fwd_begin, lp.fwd_end, s->nsm, st); count++; }
+    }
+}
+
+void enqueue_bwd(tlpb200_solver* s, int64_t& count) {
+    cudaStream_t st = s->stream;
+    const auto& L = s->plan.levels;
+    for (size_t l = L.size(); l-- > 0;) {
+        const LevelPlan& lp = L[l];
+        if (lp.bwd_end > lp.bwd_begin) { Scope sc(s, 9); launch_bwd_large((*s->cur), lp.bwd_begin, lp.bwd_end, s->nsm, st); count++; }
+        if (lp.small_end > lp.small_begin) { Scope sc(s, 11); launch_bwd_small((*s->cur), lp.small_begin, lp.small_end, st); count++; }
+    }
+}
+
+void enqueue_recover(tlpb200_solver* s, const double* xid, double* dx, double* dy, int64_t& count) {
+    cudaStream_t st = s->stream;
+    {
+        Scope sc(s, 5);
+        if (s->system == TLPB200_K1) launch_k1_recover((*s->cur), s->mat, s->d_d, xid, dx, dy, st);
+        else launch_k2_recover((*s->cur), s->mat, dx, dy, st);
+    }
+    count++;
     CK(cudaGetLastError());
 }
 
 void enqueue_solve(tlpb200_solver* s, const double* xip, const double* xid, double* dx, double* dy, int64_t& count) {
-    cudaStream_t st = s->stream;
-    {
-        Scope sc(s, 5);
-        if (s->system == TLPB200_K1) launch_k1_rhs(s->ctx, s->mat, s->d_d, xip, xid, st);
-        else launch_k2_rhs(s->ctx, s->mat, xip, xid, st);
-    }
-    count++;
-    const auto& L = s->plan.levels;
-    if (s->ctx.ndblk > 0) CK(cudaMemsetAsync(s->ctx.flags, 0, (size_t)2 * s->ctx.ndblk * sizeof(int32_t), st));
-    for (size_t l = 0; l < L.size(); ++l) {
-        const LevelPlan& lp = L[l];
-        if (lp.small_end > lp.small_begin) { Scope sc(s, 6); launch_fwd_small(s->ctx, lp.small_begin, lp.small_end, st); count++; }
-        if (lp.fwd_end > lp.fwd_begin) { Scope sc(s, 7); launch_fwd_large(s->ctx, lp.fwd_begin, lp.fwd_end, s->nsm, st); count++; }
-    }
-    for (size_t l = L.size(); l-- > 0;) {
-        const LevelPlan& lp = L[l];
-        if (lp.bwd_end > lp.bwd_begin) { Scope sc(s, 9); launch_bwd_large(s->ctx, lp.bwd_begin, lp.bwd_end, s->nsm, st); count++; }
-        if (lp.small_end > lp.small_begin) { Scope sc(s, 11); launch_bwd_small(s->ctx, lp.small_begin, lp.small_end, st); count++; }
-    }
-    {
-        Scope sc(s, 5);
-        if (s->system == TLPB200_K1) launch_k1_recover(s->ctx, s->mat, s->d_d, xid, dx, dy, st);
-        else launch_k2_recover(s->ctx, s->mat, dx, dy, st);
-    }
-    count++;
-    CK(cudaGetLastError());
+    enqueue_rhs(s, xip, xid, count);
+    enqueue_fwd(s, count);
+    enqueue_bwd(s, count);
+    enqueue_recover(s, xid, dx, dy, count);
 }
 
 void destroy_graphs(tlpb200_solver* s) {
@@ -435,6 +461,20 @@ void setup_device(tlpb200_solver* s) {
     c.info = dalloc<int32_t>(s, 4);
     c.wk = dalloc<double>(s, (size_t)S.N);
     CK(cudaMemset(c.wk, 0, std::max<size_t>(S.N, 1) * sizeof(double)));
+    c.skip = nullptr;
+    s->cur = &s->ctx;
+    if (s->nranks > 1) {
+        std::vector<int8_t> skipA(S.nsuper), skipB(S.nsuper), keep(S.N);
+        for (int32_t sn = 0; sn < S.nsuper; ++sn) {
+            skipA[sn] = (s->owner[sn] != s->rank);
+            skipB[sn] = (s->owner[sn] != -1);
+            const int8_t k = (s->owner[sn] == s->rank) || (s->owner[sn] == -1 && s->rank == 0);
+            for (int32_t j = S.sn_first[sn]; j < S.sn_first[sn + 1]; ++j) keep[j] = k;
+        }
+        s->ctxA = s->ctx; s->ctxA.skip = upload(s, skipA);
+        s->ctxB = s->ctx; s->ctxB.skip = upload(s, skipB);
+        s->d_keep = const_cast<int8_t*>(upload(s, keep));
+    }
     s->nsm = prop.multiProcessorCount;
     if (const char* e = getenv("TLPB200_CHAIN_SMS")) s->chain_sms = std::max(0, std::min(s->nsm - 1, atoi(e)));
 
@@ -494,6 +534,8 @@ void tlpb200_default_options(tlpb200_options* o) {
     o->relax_always = 8;
     o->use_graph = 1;
     o->analyze_only = 0;
+    o->rank = 0;
+    o->nranks = 1;
 }
 
 int tlpb200_create(tlpb200_solver** out, int64_t m, int64_t n, const int64_t* colptr, const int64_t* rowval,
@@ -531,6 +573,11 @@ int tlpb200_create(tlpb200_solver** out, int64_t m, int64_t n, const int64_t* co
             for (int64_t j = 0; j < n; ++j) sg[j] = -1;   // first n pivots < 0, last m > 0 (systems.jl:10-32)
             analyze_pattern(P, so, sg.data(), s->sym);
         }
+        s->rank = s->opt.rank;
+        s->nranks = std::max(1, s->opt.nranks);
+        if (s->rank < 0 || s->rank >= s->nranks) throw std::invalid_argument("rank out of range");
+        partition_subtrees(s->sym, s->nranks, s->owner);
+        if (s->nranks > 1) s->top_begin = relayout_panels(s->sym, s->owner);
         PlanOptions po;
         po.small_elems = s->opt.small_elems;
         build_plan(s->sym, po, s->plan);
@@ -752,6 +799,159 @@ int tlpb200_debug_get_lx(tlpb200_solver* s, double* lx, int64_t* xptr) {
         CK(cudaStreamSynchronize(s->stream));
         if (lx) CK(cudaMemcpy(lx, s->ctx.Lx, (size_t)s->sym.lx_size * 8, cudaMemcpyDeviceToHost));
         if (xptr) std::copy(s->sym.sn_xptr.begin(), s->sym.sn_xptr.end(), xptr);
+        return TLPB200_OK;
+    } catch (const CudaFail& f) {
+        return cuda_fail(s, f);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Multi-GPU (one process per GPU): subtree-sharded factorisation.  The caller (tulip.jl_b200/parallel.py,
+// torch.distributed / NCCL) performs the collectives between the phases on the exposed device buffers.
+// ---------------------------------------------------------------------------------------------
+int tlpb200_dist_info(const tlpb200_solver* s, int32_t* owner, int64_t* top_offset, int64_t* top_count) {
+    if (!s) return TLPB200_BAD_ARG;
+    if (owner) std::copy(s->owner.begin(), s->owner.end(), owner);
+    if (top_offset) *top_offset = s->nranks > 1 ? s->top_begin : s->sym.lx_size;
+    if (top_count) *top_count = s->nranks > 1 ? s->sym.lx_size - s->top_begin : 0;
+    return TLPB200_OK;
+}
+
+// assemble + factorisation of this rank's subtrees; leaves the partial top panels in Lx[top range]
+int tlpb200_update_begin(tlpb200_solver* s, const double* theta_inv, const double* regP, const double* regD) {
+    REQUIRE_DEVICE(s);
+    if (s->nranks < 2) return fail(s, TLPB200_BAD_ARG, "tlpb200_update_begin: solver was not created with nranks > 1");
+    try {
+        CK(cudaSetDevice(s->device));
+        const size_t n = (size_t)s->n, m = (size_t)s->m;
+        std::memcpy(s->h_pin, theta_inv, n * 8);
+        std::memcpy(s->h_pin + n, regP, n * 8);
+        std::memcpy(s->h_pin + 2 * n, regD, m * 8);
+        CK(cudaMemcpyAsync(s->d_theta, s->h_pin, n * 8, cudaMemcpyHostToDevice, s->stream));
+        CK(cudaMemcpyAsync(s->d_regP, s->h_pin + n, n * 8, cudaMemcpyHostToDevice, s->stream));
+        CK(cudaMemcpyAsync(s->d_regD, s->h_pin + 2 * n, m * 8, cudaMemcpyHostToDevice, s->stream));
+        int64_t cnt = 0;
+        s->cur = &s->ctx;
+        enqueue_assemble(s, cnt);
+        // original entries of the replicated top part are contributed by rank 0 only
+        if (s->rank != 0 && s->sym.lx_size > s->top_begin)
+            CK(cudaMemsetAsync(s->ctx.Lx + s->top_begin, 0, (size_t)(s->sym.lx_size - s->top_begin) * 8, s->stream));
+        s->cur = &s->ctxA;
+        enqueue_factor(s, cnt);
+        s->cur = &s->ctx;
+        s->launches_update = cnt;
+        CK(cudaStreamSynchronize(s->stream));
+        return TLPB200_OK;
+    } catch (const CudaFail& f) {
+        s->cur = &s->ctx;
+        return cuda_fail(s, f);
+    }
+}
+
+int tlpb200_top_panels(tlpb200_solver* s, void** dptr, int64_t* count) {
+    REQUIRE_DEVICE(s);
+    if (dptr) *dptr = s->ctx.Lx + (s->nranks > 1 ? s->top_begin : s->sym.lx_size);
+    if (count) *count = s->nranks > 1 ? s->sym.lx_size - s->top_begin : 0;
+    return TLPB200_OK;
+}
+
+// (after the all-reduce of the top panels) factorisation of the replicated top part
+int tlpb200_update_end(tlpb200_solver* s, int64_t* bad_pivot) {
+    REQUIRE_DEVICE(s);
+    if (s->nranks < 2) return fail(s, TLPB200_BAD_ARG, "tlpb200_update_end: solver was not created with nranks > 1");
+    try {
+        CK(cudaSetDevice(s->device));
+        int64_t cnt = 0;
+        CK(cudaMemsetAsync(s->lazy_ctr, 0, (2 * s->plan.levels.size() + 2) * sizeof(int32_t), s->stream));
+        s->cur = &s->ctxB;
+        enqueue_factor(s, cnt);
+        s->cur = &s->ctx;
+        s->launches_update += cnt;
+        CK(cudaMemcpyAsync(s->h_info, s->ctx.info, sizeof(int32_t), cudaMemcpyDeviceToHost, s->stream));
+        s->n_update++;
+        return finish_update(s, bad_pivot);
+    } catch (const CudaFail& f) {
+        s->cur = &s->ctx;
+        return cuda_fail(s, f);
+    }
+}
+
+// rhs build + forward sweep over this rank's subtrees; wk then holds this rank's contribution
+int tlpb200_solve_begin(tlpb200_solver* s, const double* xi_p, const double* xi_d) {
+    REQUIRE_DEVICE(s);
+    if (s->nranks < 2) return fail(s, TLPB200_BAD_ARG, "tlpb200_solve_begin: solver was not created with nranks > 1");
+    try {
+        CK(cudaSetDevice(s->device));
+        const size_t n = (size_t)s->n, m = (size_t)s->m;
+        std::memcpy(s->h_pin, xi_p, m * 8);
+        std::memcpy(s->h_pin + m, xi_d, n * 8);
+        CK(cudaMemcpyAsync(s->d_xip, s->h_pin, m * 8, cudaMemcpyHostToDevice, s->stream));
+        CK(cudaMemcpyAsync(s->d_xid, s->h_pin + m, n * 8, cudaMemcpyHostToDevice, s->stream));
+        int64_t cnt = 0;
+        s->cur = &s->ctx;
+        enqueue_rhs(s, s->d_xip, s->d_xid, cnt);
+        launch_zero_unowned(s->ctx, s->d_keep, s->stream);
+        s->cur = &s->ctxA;
+        enqueue_fwd(s, cnt);
+        s->cur = &s->ctx;
+        s->launches_solve = cnt + 1;
+        CK(cudaStreamSynchronize(s->stream));
+        return TLPB200_OK;
+    } catch (const CudaFail& f) {
+        s->cur = &s->ctx;
+        return cuda_fail(s, f);
+    }
+}
+
+int tlpb200_work_vector(tlpb200_solver* s, void** dptr, int64_t* count) {
+    REQUIRE_DEVICE(s);
+    if (dptr) *dptr = s->ctx.wk;
+    if (count) *count = s->sym.N;
+    return TLPB200_OK;
+}
+
+// (after the all-reduce of wk) top part forward + backward, then backward over this rank's subtrees;
+// wk again holds this rank's contribution (its own columns; the top part on rank 0)
+int tlpb200_solve_mid(tlpb200_solver* s) {
+    REQUIRE_DEVICE(s);
+    if (s->nranks < 2) return fail(s, TLPB200_BAD_ARG, "tlpb200_solve_mid: solver was not created with nranks > 1");
+    try {
+        CK(cudaSetDevice(s->device));
+        int64_t cnt = 0;
+        s->cur = &s->ctxB;
+        enqueue_fwd(s, cnt);
+        enqueue_bwd(s, cnt);
+        s->cur = &s->ctxA;
+        enqueue_bwd(s, cnt);
+        s->cur = &s->ctx;
+        launch_zero_unowned(s->ctx, s->d_keep, s->stream);
+        s->launches_solve += cnt + 1;
+        CK(cudaStreamSynchronize(s->stream));
+        return TLPB200_OK;
+    } catch (const CudaFail& f) {
+        s->cur = &s->ctx;
+        return cuda_fail(s, f);
+    }
+}
+
+// (after the second all-reduce of wk) recovery of dx, dy on every rank
+int tlpb200_solve_end(tlpb200_solver* s, double* dx, double* dy) {
+    REQUIRE_DEVICE(s);
+    if (s->nranks < 2) return fail(s, TLPB200_BAD_ARG, "tlpb200_solve_end: solver was not created with nranks > 1");
+    try {
+        CK(cudaSetDevice(s->device));
+        const size_t n = (size_t)s->n, m = (size_t)s->m;
+        int64_t cnt = 0;
+        s->cur = &s->ctx;
+        enqueue_recover(s, s->d_xid, s->d_dx, s->d_dy, cnt);
+        double* hout = s->h_pin + (n + m);
+        CK(cudaMemcpyAsync(hout, s->d_dx, n * 8, cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaMemcpyAsync(hout + n, s->d_dy, m * 8, cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaStreamSynchronize(s->stream));
+        std::memcpy(dx, hout, n * 8);
+        std::memcpy(dy, hout + n, m * 8);
+        s->launches_solve += cnt;
+        s->n_solve++;
         return TLPB200_OK;
     } catch (const CudaFail& f) {
         return cuda_fail(s, f);

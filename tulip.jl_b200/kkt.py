@@ -46,6 +46,8 @@ class Backend:
     relax_always: int = 8
     use_graph: bool = True
     analyze_only: bool = False  # host symbolic analysis only (CPU tests); numeric calls then fail
+    rank: int = 0               # multi-GPU subtree sharding (tulip.jl_b200/parallel.py sets these)
+    nranks: int = 1
 
 
 # ---- exceptions (what the reference throws at this boundary) ---------------------------------
@@ -107,6 +109,8 @@ class B200KKTSolver:
         opt.relax_always = backend.relax_always
         opt.use_graph = 1 if backend.use_graph else 0
         opt.analyze_only = 1 if backend.analyze_only else 0
+        opt.rank = backend.rank
+        opt.nranks = backend.nranks
         colptr = np.ascontiguousarray(A.indptr, dtype=np.int64)
         rowval = np.ascontiguousarray(A.indices, dtype=np.int64)
         nzval = np.ascontiguousarray(A.data, dtype=np.float64)
@@ -224,6 +228,14 @@ class B200KKTSolver:
         rows = np.zeros(int(rowptr[-1]), np.int32)
         _lib.load().tlpb200_get_structure(self._h, None, vp(rows))
         return dict(perm=perm, parent=parent, colcount=cc, sn_first=first, sn_rowptr=rowptr, sn_rows=rows)
+
+    def dist_info(self):
+        """owner[s] (rank or -1 = replicated top part), offset and length of the top panels in Lx."""
+        ns = self.stats()["nsuper"]
+        owner = np.zeros(ns, np.int32)
+        off = C.c_int64(0); cnt = C.c_int64(0)
+        _lib.load().tlpb200_dist_info(self._h, C.c_void_p(owner.ctypes.data), C.byref(off), C.byref(cnt))
+        return owner, off.value, cnt.value
 
     def debug_assembled(self, theta_inv, regP, regD):
         """Assemble only (no factorisation) and return (Lx, xptr) -- parity test of the assemble kernel."""
