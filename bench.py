@@ -52,6 +52,10 @@ def build_lp(cfg):
         return pkg, lpgen.config(2), "K1"
     if cfg == "3":
         return pkg, lpgen.config(3), "K2"
+    if cfg == "4":
+        return pkg, lpgen.config(4), "K1"
+    if cfg == "4mini":
+        return pkg, lpgen.config(4, mini=True), "K1"
     if cfg == "T":
         return pkg, lpgen.config("T"), "K1"
     if cfg == "mini":
@@ -172,10 +176,12 @@ def gpu_arm(args):
     A = lp.A
     m, n = A.shape
     sy = pkg.K1() if sysname == "K1" else pkg.K2()
+    K, W = args.steps, args.warmup
+    if world > 1 and args.config.startswith("4"):
+        return sharded_arm(args, pkg, lp, sysname, sy, dist, rank, world, local)
     t0 = time.time()
     kkt = pkg.setup(A, sy, pkg.Backend(device=local))
     t_setup = time.time() - t0
-    K, W = args.steps, args.warmup
     # ---- pass 1: the real IPM through the host API (e2e) ------------------------------------
     sampler = ClockSampler(local)
     h, recs = record_hsd(pkg, lp, kkt, W + K)
@@ -293,6 +299,58 @@ def gpu_arm(args):
     if dist:
         dist.barrier()
         dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+
+
+def sharded_arm(args, pkg, lp, sysname, sy, dist, rank, world, local):
+    """BASELINE configs[3]: block-angular LP, elimination-tree subtrees sharded across the ranks, NCCL all-reduce of
+    the separator front (tulip.jl_b200/parallel.py).  Every rank runs the same IPM (SPMD); timing = sum of the
+    KKT calls of the timed iterations through the host API, max over ranks.  Strong scaling: the job is fixed."""
+    import torch
+    from tulip_jl_b200 import parallel
+    K, W = args.steps, args.warmup
+    t0 = time.time()
+    kkt = parallel.DistB200KKT(lp.A, sy, pkg.Backend(device=local))
+    t_setup = time.time() - t0
+    sampler = ClockSampler(local)
+    dist.barrier(); torch.cuda.synchronize()
+    sampler.start()
+    h, recs = record_hsd(pkg, lp, kkt, W + K)
+    torch.cuda.synchronize(); dist.barrier()
+    clocks = sampler.stop()
+    base = len(recs)
+    if base < W + 1:
+        raise SystemExit("IPM terminated during warm-up; lower --warmup")
+    timed = recs[W:min(base, W + K)]
+    k_done = len(timed)
+    t = torch.tensor([sum(r["t_update"] + r["t_solve"] for r in timed)], dtype=torch.float64, device=f"cuda:{local}")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    tot = float(t[0])
+    nsolve = float(np.mean([len(r["rhs"]) for r in timed]))
+    st = kkt.stats()
+    owner, off, cnt = kkt.dist_info()
+    m, n = lp.A.shape
+    val = k_done / tot
+    out = {"metric": METRIC, "value": round(val, 4), "unit": UNIT, "n_gpus": world, "steps": k_done, "warmup": W,
+           "ms_per_step": round(tot * 1e3 / k_done, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic",
+           "config": {"workload": workload_name(lp, sysname, nsolve),
+                      "parallelism": f"etree subtrees sharded over {world} ranks + NCCL all-reduce of the separator panels "
+                                     f"({cnt * 8 / 1e6:.2f} MB per update!, {2 * 8 * st['order'] / 1e6:.2f} MB per solve!)",
+                      "l2": "timed through the host-pointer API (H2D/D2H inside); factor panels exceed L2",
+                      "nnzL": st["nnzL"], "factor_flops": st["flops"], "setup_s": round(t_setup, 2),
+                      "ipm_status_after": h.status, "ipm_iters_run": h.niter},
+           "clocks": clocks,
+           "e2e": {"value": round(val, 4), "unit": UNIT, "h2d_bytes_per_step": int((2 * n + m) * 8 + nsolve * (n + m) * 8),
+                   "d2h_bytes_per_step": int(4 + nsolve * (n + m) * 8), "ms_per_step": round(tot * 1e3 / k_done, 4)},
+           "gpu_launches": int(k_done * (st["launches_update"] + nsolve * st["launches_solve"])),
+           "roofline": {"bound": "tensor", "achieved": None, "peak": None, "unit": "TFLOP/s", "frac": None, "traffic": None,
+                        "note": "per-kernel roofline is reported by the single-GPU run (--gpus 1)"},
+           "update_ms_host_api": round(float(np.mean([r["t_update"] for r in timed])) * 1e3, 3),
+           "solve_ms_host_api": round(float(np.sum([r["t_solve"] for r in timed]) / np.sum([len(r["rhs"]) for r in timed])) * 1e3, 3)}
+    dist.barrier()
+    dist.destroy_process_group()
     if rank == 0:
         print(json.dumps(out), flush=True)
 
