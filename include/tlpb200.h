@@ -50,7 +50,9 @@ typedef struct tlpb200_options {
     int32_t use_graph;     /* 1 = replay update!/solve! as CUDA graphs (default 1) */
     int32_t analyze_only;  /* 1 = host symbolic analysis only, no device is touched (tests, no GPU) */
     int32_t rank, nranks;  /* multi-GPU subtree sharding: this process's rank and the world size (default 0, 1) */
-    int32_t reserved[7];
+    int32_t dense_col_threshold; /* K1: columns with more non-zeros are handled by a low-rank Schur correction;
+                                    0 = auto (max(32, 5% of m)), < 0 = off */
+    int32_t reserved[6];
 } tlpb200_options;
 
 typedef struct tlpb200_stats {
@@ -136,6 +138,9 @@ int tlpb200_solve_begin(tlpb200_solver* s, const double* xi_p, const double* xi_
 int tlpb200_work_vector(tlpb200_solver* s, void** dptr, int64_t* count);
 int tlpb200_solve_mid(tlpb200_solver* s);
 int tlpb200_solve_end(tlpb200_solver* s, double* dx, double* dy);
+
+/* K1 dense-column path: number and (0-based) indices of the columns kept out of the sparse factor */
+int tlpb200_get_dense_cols(const tlpb200_solver* s, int32_t* count, int64_t* cols /* may be NULL */);
 
 const char* tlpb200_last_error(const tlpb200_solver* s);
 const char* tlpb200_backend_name(void);            /* KKT.backend(kkt)       (KKT.jl:114) */

@@ -67,7 +67,12 @@ def test_assemble_and_factor_parity(cfg, sysname):
     rng = np.random.default_rng(11)
     theta = np.exp(rng.uniform(-5, 5, n)); regP = np.full(n, 1e-7); regD = np.full(m, 1e-7)
     k = pkg.setup(lp.A, SYSTEMS[sysname](), pkg.Backend())
-    K = _kkt_matrix(lp.A, sysname, theta, regP, regD)
+    Aeff = lp.A
+    dc = k.dense_cols()
+    if len(dc):      # K1 dense-column path: the sparse factor holds A_s D_s A_s' + Rd only
+        keep = np.ones(n); keep[dc] = 0.0
+        Aeff = (lp.A @ sp.diags(keep)).tocsc()
+    K = _kkt_matrix(Aeff, sysname, theta, regP, regD)
     lx, xptr = k.debug_assembled(theta, regP, regD)
     Lasm, sym = _dense_from_lx(k, lx, xptr)
     p = sym["perm"]
@@ -274,3 +279,56 @@ def test_full_size_properties(cfg, sysname):
         xs.append(np.concatenate([dx, dy]))
     comb = 2.0 * xs[0] - 3.0 * xs[1]
     assert np.abs(xs[2] - comb).max() <= 1e-7 * max(1.0, np.abs(comb).max())
+
+
+def test_dense_column_schur_path():
+    """BASELINE config 5: K1 with dense columns handled by the low-rank Schur correction == oracle on the FULL
+    matrix (the reference itself would form a dense A*D*A', spd.jl:43) == the same backend with the path disabled."""
+    lp = lpgen.config(5, mini=True)
+    A = lp.A
+    m, n = A.shape
+    rng = np.random.default_rng(12)
+    theta = np.exp(rng.uniform(-3, 3, n)); regP = np.full(n, 1e-5); regD = np.full(m, 1e-5)
+    xi_p = rng.standard_normal(m); xi_d = rng.standard_normal(n)
+    k = pkg.setup(A, pkg.K1(), pkg.Backend())
+    assert len(k.dense_cols()) == 3
+    k_off = pkg.setup(A, pkg.K1(), pkg.Backend(dense_col_threshold=-1))
+    assert len(k_off.dense_cols()) == 0
+    assert k.stats()["nnzL"] < 0.5 * k_off.stats()["nnzL"]          # the point of the exercise: far less fill
+    o = kkt_ref.DenseK1(A)
+    sols = []
+    for kk in (k, k_off, o):
+        kk.update(theta, regP, regD)
+        dx = np.zeros(n); dy = np.zeros(m)
+        kk.solve(dx, dy, xi_p, xi_d)
+        rp, rd = kkt_ref.kkt_residuals(A, theta, regP, regD, dx, dy, xi_p, xi_d)
+        assert rp <= 1e-9 and rd <= 1e-9
+        sols.append(np.concatenate([dx, dy]))
+    for s_ in sols[:2]:
+        assert np.abs(s_ - sols[2]).max() <= 1e-8 * np.abs(sols[2]).max()
+    # end to end: the IPM converges to the same objective with and without the path
+    objs = []
+    for be in (pkg.Backend(), pkg.Backend(dense_col_threshold=-1)):
+        kkt = pkg.setup(A, pkg.K1(), be)
+        h = hsd.HSD(A, lp.b, lp.c, lp.l, lp.u, kkt)
+        assert h.optimize() == "Trm_Optimal"
+        objs.append(h.primal_objective)
+    assert abs(objs[0] - objs[1]) <= 1e-7 * (1 + abs(objs[1]))
+
+
+def test_dense_columns_full_size():
+    """config 5 at BASELINE size (m=5e4, n=1e5, 8 columns of 25 000 non-zeros): KKT residuals of the full system."""
+    lp = lpgen.config(5)
+    A = lp.A
+    m, n = A.shape
+    rng = np.random.default_rng(13)
+    theta = np.exp(rng.uniform(-3, 3, n)); regP = np.full(n, 1e-6); regD = np.full(m, 1e-6)
+    k = pkg.setup(A, pkg.K1(), pkg.Backend())
+    assert len(k.dense_cols()) == 8
+    k.update(theta, regP, regD)
+    xi_p = rng.standard_normal(m); xi_d = rng.standard_normal(n)
+    dx = np.zeros(n); dy = np.zeros(m)
+    k.solve(dx, dy, xi_p, xi_d)
+    rp, rd = kkt_ref.kkt_residuals(A, theta, regP, regD, dx, dy, xi_p, xi_d)
+    scale = max(1.0, np.abs(dx).max(), np.abs(dy).max())
+    assert rp <= SQRT_EPS * scale and rd <= SQRT_EPS * scale

@@ -39,7 +39,15 @@ def _check(A, sysname):
     N = st["order"]
     assert N == (A.shape[0] if sysname == "K1" else sum(A.shape))
     assert sorted(sym["perm"].tolist()) == list(range(N))
-    S = sr.kkt_pattern(A, sysname)
+    dc = k.dense_cols()                      # K1: columns kept out of the sparse factor (low-rank Schur path)
+    assert sysname == "K1" or len(dc) == 0
+    Aeff = sp.csc_matrix(A)
+    if len(dc):
+        keep = np.ones(A.shape[1]); keep[dc] = 0.0
+        Aeff = (Aeff @ sp.diags(keep)).tocsc(); Aeff.eliminate_zeros()
+        nnzcol = np.diff(sp.csc_matrix(A).indptr)
+        assert nnzcol[dc].min() > max(32, 0.05 * A.shape[0]) and len(dc) <= 64
+    S = sr.kkt_pattern(Aeff, sysname)
     parent, cc, struct = sr.symbolic_bruteforce(S, sym["perm"])
     assert np.array_equal(parent, sym["parent"]), "elimination tree differs"
     assert np.array_equal(cc, sym["colcount"]), "column counts differ"

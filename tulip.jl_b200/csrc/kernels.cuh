@@ -66,6 +66,25 @@ struct DevMat {
     const int64_t* a_dest;
 };
 
+// dense columns of A handled outside the sparse factorisation (K1 only, see kernels_dense_cols.cu)
+struct DenseCols {
+    int32_t nd;
+    const int64_t* colptr;   // [nd+1] into prow / val
+    const int32_t* prow;     // permuted row index of every entry
+    const double* val;
+    const int32_t* col_id;   // [nd] original column index
+    double* V;               // [nd][N]   K_s^{-1} A_d, permuted order
+    double* C;               // [nd*nd]   Gram matrix, then its Cholesky factor (row-major lower)
+    double* g;               // [nd]
+};
+void launch_dc_scatter(const DevCtx& c, const DenseCols& dc, int j, int64_t colnnz, cudaStream_t st);
+void launch_dc_gram_chol(const DevCtx& c, const DenseCols& dc, const double* theta, const double* regP, cudaStream_t st);
+void launch_dc_apply(const DevCtx& c, const DenseCols& dc, cudaStream_t st);
+struct DevMat;
+void launch_dc_residual(const DevCtx& c, const DevMat& A, const double* d, const double* regD, const double* xi, const double* y,
+                        double* tn, cudaStream_t st);
+void launch_dc_axpy(const DevCtx& c, const double* y, cudaStream_t st);
+
 // ---- launchers (all asynchronous on `st`) ---------------------------------------------------
 void launch_compute_d(const double* theta, const double* regP, double* d, int64_t n, cudaStream_t st);
 void launch_assemble_k1(const DevCtx& c, const DevMat& A, const double* d, const double* regD, cudaStream_t st);

@@ -1,0 +1,151 @@
+// Dense-column handling for the normal equations (BASELINE config 5; a capability the reference lacks:
+// with K1 its A*D*A' simply becomes dense, /root/reference/src/KKT/Cholmod/spd.jl:43).
+//
+//   A = [A_s  A_d],  K = A_s D_s A_s' + Rd + A_d D_d A_d' = K_s + A_d D_d A_d'
+// K_s keeps the sparse factorisation; the nd dense columns enter through the Schur complement of the
+// bordered system (Sherman-Morrison-Woodbury):
+//   V = K_s^{-1} A_d               (nd sparse solves per update!)
+//   C = D_d^{-1} + A_d' V          (nd x nd, SPD), C = Lc Lc'
+//   K^{-1} b = y0 - V C^{-1} (A_d' y0),   y0 = K_s^{-1} b
+#include "kernels.cuh"
+
+namespace tlp {
+
+__device__ __forceinline__ double block_sum(double v, double* red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    return t;
+}
+
+// wk = A_d(:, j) in permuted row order (wk must be zero on entry)
+__global__ void k_dc_scatter(DevCtx c, DenseCols dc, int j) {
+    const int64_t p = dc.colptr[j] + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p < dc.colptr[j + 1]) c.wk[dc.prow[p]] = dc.val[p];
+}
+
+// C[i][j] = A_d(:,i)' V_j  (+ theta+regP of dense column i on the diagonal = D_d^{-1})
+__global__ void k_dc_gram(DevCtx c, DenseCols dc, const double* __restrict__ theta, const double* __restrict__ regP) {
+    __shared__ double red[32];
+    const int i = blockIdx.x, j = blockIdx.y;
+    const double* Vj = dc.V + (int64_t)j * c.N;
+    double a = 0.0;
+    for (int64_t p = dc.colptr[i] + threadIdx.x; p < dc.colptr[i + 1]; p += blockDim.x) a += dc.val[p] * Vj[dc.prow[p]];
+    a = block_sum(a, red);
+    if (threadIdx.x == 0) {
+        if (i == j) a += theta[dc.col_id[i]] + regP[dc.col_id[i]];
+        dc.C[i * dc.nd + j] = a;
+    }
+}
+
+// in-place Cholesky of the nd x nd matrix C (one block; nd <= 64)
+__global__ void k_dc_chol(DevCtx c, DenseCols dc) {
+    __shared__ double Cs[64 * 65];
+    const int nd = dc.nd, tid = threadIdx.x;
+    for (int e = tid; e < nd * nd; e += blockDim.x) Cs[(e / nd) * 65 + (e % nd)] = 0.5 * (dc.C[e] + dc.C[(e % nd) * nd + e / nd]);
+    for (int j = 0; j < nd; ++j) {
+        __syncthreads();
+        double d = Cs[j * 65 + j];
+        if (!(d > 0.0)) {
+            if (tid == 0) atomicMin(c.info, c.N - 1);
+            d = 1.0;
+        }
+        const double l = sqrt(d);
+        __syncthreads();
+        for (int i = j + tid; i < nd; i += blockDim.x) Cs[i * 65 + j] = (i == j) ? l : Cs[i * 65 + j] / l;
+        __syncthreads();
+        for (int e = tid; e < (nd - j - 1) * (nd - j - 1); e += blockDim.x) {
+            const int i = j + 1 + e / (nd - j - 1), k = j + 1 + e % (nd - j - 1);
+            if (i >= k) Cs[i * 65 + k] -= Cs[i * 65 + j] * Cs[k * 65 + j];
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < nd * nd; e += blockDim.x) {
+        const int i = e / nd, k = e % nd;
+        dc.C[e] = (i >= k) ? Cs[i * 65 + k] : 0.0;     // row-major lower factor Lc
+    }
+}
+
+// g[i] = A_d(:,i)' wk
+__global__ void k_dc_dots(DevCtx c, DenseCols dc) {
+    __shared__ double red[32];
+    const int i = blockIdx.x;
+    double a = 0.0;
+    for (int64_t p = dc.colptr[i] + threadIdx.x; p < dc.colptr[i + 1]; p += blockDim.x) a += dc.val[p] * c.wk[dc.prow[p]];
+    a = block_sum(a, red);
+    if (threadIdx.x == 0) dc.g[i] = a;
+}
+
+// t = C^{-1} g (every block redundantly, nd <= 64), then wk -= sum_i V_i t_i
+__global__ void k_dc_apply(DevCtx c, DenseCols dc) {
+    __shared__ double t[64];
+    const int nd = dc.nd;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < nd; ++i) {                      // Lc y = g
+            double a = dc.g[i];
+            for (int k = 0; k < i; ++k) a -= dc.C[i * nd + k] * t[k];
+            t[i] = a / dc.C[i * nd + i];
+        }
+        for (int i = nd - 1; i >= 0; --i) {                 // Lc' t = y
+            double a = t[i];
+            for (int k = i + 1; k < nd; ++k) a -= dc.C[k * nd + i] * t[k];
+            t[i] = a / dc.C[i * nd + i];
+        }
+    }
+    __syncthreads();
+    const int32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= c.N) return;
+    double a = 0.0;
+    for (int i = 0; i < nd; ++i) a += dc.V[(int64_t)i * c.N + q] * t[i];
+    c.wk[q] -= a;
+}
+
+// ---- iterative refinement on the full normal equations (the Woodbury correction alone loses accuracy when K_s is
+// ill-conditioned, which it is near IPM convergence):  r = xi - (A D A' + Rd) y, all in permuted row order
+__global__ void k_dc_at_y(DevCtx c, DevMat A, const double* __restrict__ d, const double* __restrict__ y, double* __restrict__ tn) {
+    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j >= A.n) return;
+    double v = 0.0;
+    for (int64_t p = A.colptr[j]; p < A.colptr[j + 1]; ++p) v += A.val[p] * y[c.iperm[A.rowidx[p]]];
+    tn[j] = d[j] * v;
+}
+__global__ void k_dc_residual(DevCtx c, DevMat A, const double* __restrict__ regD, const double* __restrict__ xi,
+                              const double* __restrict__ y, const double* __restrict__ tn) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= A.m) return;
+    const int32_t q = c.iperm[i];
+    double v = xi[q] - regD[i] * y[q];
+    for (int64_t p = A.rowptr[i]; p < A.rowptr[i + 1]; ++p) v -= A.rval[p] * tn[A.colidx[p]];
+    c.wk[q] = v;
+}
+__global__ void k_dc_axpy(DevCtx c, const double* __restrict__ y) {
+    const int32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < c.N) c.wk[q] += y[q];
+}
+void launch_dc_residual(const DevCtx& c, const DevMat& A, const double* d, const double* regD, const double* xi, const double* y,
+                        double* tn, cudaStream_t st) {
+    k_dc_at_y<<<(unsigned)((A.n + 127) / 128), 128, 0, st>>>(c, A, d, y, tn);
+    k_dc_residual<<<(unsigned)((A.m + 127) / 128), 128, 0, st>>>(c, A, regD, xi, y, tn);
+}
+void launch_dc_axpy(const DevCtx& c, const double* y, cudaStream_t st) {
+    k_dc_axpy<<<(c.N + 255) / 256, 256, 0, st>>>(c, y);
+}
+
+void launch_dc_scatter(const DevCtx& c, const DenseCols& dc, int j, int64_t colnnz, cudaStream_t st) {
+    if (colnnz > 0) k_dc_scatter<<<(unsigned)((colnnz + 255) / 256), 256, 0, st>>>(c, dc, j);
+}
+void launch_dc_gram_chol(const DevCtx& c, const DenseCols& dc, const double* theta, const double* regP, cudaStream_t st) {
+    k_dc_gram<<<dim3(dc.nd, dc.nd), 256, 0, st>>>(c, dc, theta, regP);
+    k_dc_chol<<<1, 256, 0, st>>>(c, dc);
+}
+void launch_dc_apply(const DevCtx& c, const DenseCols& dc, cudaStream_t st) {
+    k_dc_dots<<<dc.nd, 256, 0, st>>>(c, dc);
+    k_dc_apply<<<(c.N + 255) / 256, 256, 0, st>>>(c, dc);
+}
+
+}  // namespace tlp

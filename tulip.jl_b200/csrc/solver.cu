@@ -73,6 +73,12 @@ struct tlpb200_solver {
     int64_t launches_update = 0, launches_solve = 0;
     double ms_assemble = 0, ms_factor = 0, ms_solve = 0;
     int64_t bad_pivot = -1, n_update = 0, n_solve = 0;
+    // dense columns (K1): kept out of the sparse factor, applied as a low-rank Schur correction
+    std::vector<int32_t> dense_cols;
+    std::vector<int64_t> dc_colptr;
+    DenseCols dc{};
+    double *dc_xi = nullptr, *dc_y = nullptr, *dc_tn = nullptr;   // refinement work vectors
+    int dc_refine = 2;
     std::string err;
 };
 
@@ -133,7 +139,7 @@ struct Scope {
 
 void collect_profile(tlpb200_solver* s, bool reset_update_classes) {
     // called after a stream sync
-    static const bool is_update_class[16] = {1, 1, 1, 1, 1, 0, 0, 0, 1, 0, 1, 0, 0, 0, 0, 0};
+    static const bool is_update_class[16] = {1, 1, 1, 1, 1, 0, 0, 0, 1, 0, 1, 0, 0, 0, 0, 0};   // class 12 (dense cols) is left cumulative
     for (int c = 0; c < 16; ++c)
         if (is_update_class[c] == reset_update_classes) { s->ms_class[c] = 0; s->n_class[c] = 0; }
     for (size_t i = 0; i + 1 < s->pool_used; i += 2) {
@@ -176,6 +182,9 @@ void enqueue_assemble(tlpb200_solver* s, int64_t& count) {
 // Concurrent updates into the same ancestor entries are resolved by RED.ADD.F64, which is also the
 // faster epilogue on its own: 12.7 ms vs 17.7 ms per cfg2 factorisation for read-modify-write.
 // Profiling mode and TLPB200_NO_OVERLAP=1 use the single-stream order.
+void enqueue_fwd(tlpb200_solver* s, int64_t& count);
+void enqueue_bwd(tlpb200_solver* s, int64_t& count);
+
 void enqueue_factor(tlpb200_solver* s, int64_t& count) {
     cudaStream_t st = s->stream;
     static const bool no_overlap_env = getenv("TLPB200_NO_OVERLAP") != nullptr;
@@ -228,6 +237,21 @@ void enqueue_factor(tlpb200_solver* s, int64_t& count) {
     }
     if (overlap && last_lazy > waited) CK(cudaStreamWaitEvent(st, s->ev_lazy[last_lazy], 0));   // join
     if ((*s->cur).ndblk > 0) { Scope sc(s, 10); launch_invert_diag((*s->cur), st); count++; }
+    if (s->dc.nd > 0) {
+        // V = K_s^{-1} A_d : one sparse solve per dense column, then the nd x nd Schur matrix and its Cholesky factor
+        Scope sc(s, 12);
+        for (int j = 0; j < s->dc.nd; ++j) {
+            CK(cudaMemsetAsync(s->ctx.wk, 0, (size_t)s->sym.N * 8, st));
+            if (s->ctx.ndblk > 0) CK(cudaMemsetAsync(s->ctx.flags, 0, (size_t)2 * s->ctx.ndblk * sizeof(int32_t), st));
+            launch_dc_scatter(s->ctx, s->dc, j, s->dc_colptr[j + 1] - s->dc_colptr[j], st);
+            enqueue_fwd(s, count);
+            enqueue_bwd(s, count);
+            CK(cudaMemcpyAsync(s->dc.V + (size_t)j * s->sym.N, s->ctx.wk, (size_t)s->sym.N * 8, cudaMemcpyDeviceToDevice, st));
+            count++;
+        }
+        launch_dc_gram_chol(s->ctx, s->dc, s->d_theta, s->d_regP, st);
+        count += 2;
+    }
     CK(cudaGetLastError());
 }
 
@@ -275,8 +299,26 @@ void enqueue_recover(tlpb200_solver* s, const double* xid, double* dx, double* d
 
 void enqueue_solve(tlpb200_solver* s, const double* xip, const double* xid, double* dx, double* dy, int64_t& count) {
     enqueue_rhs(s, xip, xid, count);
+    const size_t nb = (size_t)s->sym.N * 8;
+    if (s->dc.nd > 0) CK(cudaMemcpyAsync(s->dc_xi, s->ctx.wk, nb, cudaMemcpyDeviceToDevice, s->stream));
     enqueue_fwd(s, count);
     enqueue_bwd(s, count);
+    if (s->dc.nd > 0) {
+        Scope sc(s, 12);
+        launch_dc_apply(s->ctx, s->dc, s->stream);
+        count += 2;
+        // iterative refinement on the full system with the Woodbury solve as the preconditioner
+        for (int it = 0; it < s->dc_refine; ++it) {
+            CK(cudaMemcpyAsync(s->dc_y, s->ctx.wk, nb, cudaMemcpyDeviceToDevice, s->stream));
+            launch_dc_residual(s->ctx, s->mat, s->d_d, s->d_regD, s->dc_xi, s->dc_y, s->dc_tn, s->stream);
+            if (s->ctx.ndblk > 0) CK(cudaMemsetAsync(s->ctx.flags, 0, (size_t)2 * s->ctx.ndblk * sizeof(int32_t), s->stream));
+            enqueue_fwd(s, count);
+            enqueue_bwd(s, count);
+            launch_dc_apply(s->ctx, s->dc, s->stream);
+            launch_dc_axpy(s->ctx, s->dc_y, s->stream);
+            count += 5;
+        }
+    }
     enqueue_recover(s, xid, dx, dy, count);
 }
 
@@ -506,6 +548,29 @@ void setup_device(tlpb200_solver* s) {
     A.w_col = upload(s, s->maps.w_col);
     A.w_val = upload(s, s->maps.w_val);
     A.a_dest = upload(s, s->maps.a_dest);
+    if (!s->dense_cols.empty()) {
+        const int nd = (int)s->dense_cols.size();
+        std::vector<int32_t> prow;
+        std::vector<double> dval;
+        s->dc_colptr.assign(nd + 1, 0);
+        for (int i = 0; i < nd; ++i) {
+            const int32_t j = s->dense_cols[i];
+            for (int64_t p = s->colptr[j]; p < s->colptr[j + 1]; ++p) { prow.push_back(S.iperm[s->rowidx[p]]); dval.push_back(s->val[p]); }
+            s->dc_colptr[i + 1] = (int64_t)prow.size();
+        }
+        s->dc.nd = nd;
+        s->dc.colptr = upload(s, s->dc_colptr);
+        s->dc.prow = upload(s, prow);
+        s->dc.val = upload(s, dval);
+        s->dc.col_id = upload(s, s->dense_cols);
+        s->dc.V = dalloc<double>(s, (size_t)nd * S.N);
+        s->dc.C = dalloc<double>(s, (size_t)nd * nd);
+        s->dc.g = dalloc<double>(s, nd);
+        s->dc_xi = dalloc<double>(s, S.N);
+        s->dc_y = dalloc<double>(s, S.N);
+        s->dc_tn = dalloc<double>(s, s->n);
+        if (const char* e = getenv("TLPB200_DC_REFINE")) s->dc_refine = std::max(0, atoi(e));
+    }
 
     s->d_theta = dalloc<double>(s, s->n);
     s->d_regP = dalloc<double>(s, s->n);
@@ -564,8 +629,32 @@ int tlpb200_create(tlpb200_solver** out, int64_t m, int64_t n, const int64_t* co
         s->sym.system = system;
         s->sym.m = m;
         s->sym.n = n;
+        // dense columns (K1 only): more than max(32, 5% of m) non-zeros, at most 64 of them
+        std::vector<int64_t> fcolptr;       // A with the dense columns emptied (pattern + assemble use this)
+        std::vector<int32_t> frowidx;
+        std::vector<double> fval;
+        if (system == TLPB200_K1 && s->opt.dense_col_threshold >= 0 && std::max(1, s->opt.nranks) == 1) {
+            const int64_t thr = s->opt.dense_col_threshold > 0 ? s->opt.dense_col_threshold
+                                                               : std::max<int64_t>(32, (int64_t)(0.05 * (double)m));
+            for (int64_t j = 0; j < n && s->dense_cols.size() < 64; ++j)
+                if (s->colptr[j + 1] - s->colptr[j] > thr) s->dense_cols.push_back((int32_t)j);
+        }
+        const int64_t* cp_f = s->colptr.data();
+        const int32_t* ri_f = s->rowidx.data();
+        const double* va_f = s->val.data();
+        if (!s->dense_cols.empty()) {
+            std::vector<char> isd(n, 0);
+            for (int32_t j : s->dense_cols) isd[j] = 1;
+            fcolptr.assign(n + 1, 0);
+            for (int64_t j = 0; j < n; ++j) {
+                if (!isd[j])
+                    for (int64_t p = s->colptr[j]; p < s->colptr[j + 1]; ++p) { frowidx.push_back(s->rowidx[p]); fval.push_back(s->val[p]); }
+                fcolptr[j + 1] = (int64_t)frowidx.size();
+            }
+            cp_f = fcolptr.data(); ri_f = frowidx.data(); va_f = fval.data();
+        }
         if (system == TLPB200_K1) {
-            SymPattern P = pattern_k1(m, n, s->colptr.data(), s->rowidx.data());
+            SymPattern P = pattern_k1(m, n, cp_f, ri_f);
             analyze_pattern(P, so, nullptr, s->sym);
         } else {
             SymPattern P = pattern_k2(m, n, s->colptr.data(), s->rowidx.data());
@@ -582,7 +671,7 @@ int tlpb200_create(tlpb200_solver** out, int64_t m, int64_t n, const int64_t* co
         po.small_elems = s->opt.small_elems;
         build_plan(s->sym, po, s->plan);
         if (system == TLPB200_K1)
-            build_assembly_k1(s->sym, m, n, s->colptr.data(), s->rowidx.data(), s->val.data(), s->maps);
+            build_assembly_k1(s->sym, m, n, cp_f, ri_f, va_f, s->maps);
         else
             build_assembly_k2(s->sym, m, n, s->colptr.data(), s->rowidx.data(), s->maps);
         if (!s->opt.analyze_only) setup_device(s);
@@ -956,6 +1045,13 @@ int tlpb200_solve_end(tlpb200_solver* s, double* dx, double* dy) {
     } catch (const CudaFail& f) {
         return cuda_fail(s, f);
     }
+}
+
+int tlpb200_get_dense_cols(const tlpb200_solver* s, int32_t* count, int64_t* cols) {
+    if (!s) return TLPB200_BAD_ARG;
+    if (count) *count = (int32_t)s->dense_cols.size();
+    if (cols) for (size_t i = 0; i < s->dense_cols.size(); ++i) cols[i] = s->dense_cols[i];
+    return TLPB200_OK;
 }
 
 const char* tlpb200_last_error(const tlpb200_solver* s) { return s ? s->err.c_str() : "null solver"; }

@@ -41,8 +41,8 @@ end
 struct COptions
     ordering::Int32; device::Int32; piece_width::Int32; small_elems::Int32
     relax_always::Int32; use_graph::Int32; analyze_only::Int32
-    rank::Int32; nranks::Int32
-    reserved::NTuple{7,Int32}
+    rank::Int32; nranks::Int32; dense_col_threshold::Int32
+    reserved::NTuple{6,Int32}
 end
 
 mutable struct B200Solver{S<:AbstractKKTSystem} <: AbstractKKTSolver{Float64}
@@ -54,7 +54,7 @@ mutable struct B200Solver{S<:AbstractKKTSystem} <: AbstractKKTSolver{Float64}
     function B200Solver{S}(A::SparseMatrixCSC{Float64,Int}, sys::Int, b::Backend) where {S}
         m, n = size(A)
         opt = Ref(COptions(b.ordering, b.device, b.piece_width, b.small_elems, b.relax_always,
-                           b.use_graph ? 1 : 0, 0, 0, 1, ntuple(_ -> Int32(0), 7)))
+                           b.use_graph ? 1 : 0, 0, 0, 1, 0, ntuple(_ -> Int32(0), 6)))
         h = Ref{Ptr{Cvoid}}(C_NULL)
         rc = ccall((:tlpb200_create, libtlpb200), Cint,
                    (Ref{Ptr{Cvoid}}, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Cint, Cint, Ref{COptions}),

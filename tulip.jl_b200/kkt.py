@@ -48,6 +48,7 @@ class Backend:
     analyze_only: bool = False  # host symbolic analysis only (CPU tests); numeric calls then fail
     rank: int = 0               # multi-GPU subtree sharding (tulip.jl_b200/parallel.py sets these)
     nranks: int = 1
+    dense_col_threshold: int = 0  # K1 dense-column Schur path: 0 auto (max(32, 5% of m)), < 0 off
 
 
 # ---- exceptions (what the reference throws at this boundary) ---------------------------------
@@ -111,6 +112,7 @@ class B200KKTSolver:
         opt.analyze_only = 1 if backend.analyze_only else 0
         opt.rank = backend.rank
         opt.nranks = backend.nranks
+        opt.dense_col_threshold = backend.dense_col_threshold
         colptr = np.ascontiguousarray(A.indptr, dtype=np.int64)
         rowval = np.ascontiguousarray(A.indices, dtype=np.int64)
         nzval = np.ascontiguousarray(A.data, dtype=np.float64)
@@ -228,6 +230,15 @@ class B200KKTSolver:
         rows = np.zeros(int(rowptr[-1]), np.int32)
         _lib.load().tlpb200_get_structure(self._h, None, vp(rows))
         return dict(perm=perm, parent=parent, colcount=cc, sn_first=first, sn_rowptr=rowptr, sn_rows=rows)
+
+    def dense_cols(self):
+        """indices of the columns handled by the low-rank Schur correction (K1 only)"""
+        cnt = C.c_int32(0)
+        _lib.load().tlpb200_get_dense_cols(self._h, C.byref(cnt), None)
+        ids = np.zeros(cnt.value, np.int64)
+        if cnt.value:
+            _lib.load().tlpb200_get_dense_cols(self._h, C.byref(cnt), ids.ctypes.data_as(C.POINTER(C.c_int64)))
+        return ids
 
     def dist_info(self):
         """owner[s] (rank or -1 = replicated top part), offset and length of the top panels in Lx."""
