@@ -215,6 +215,21 @@ __global__ void __launch_bounds__(INV_THREADS) k_invert_diag(DevCtx c) {
         const int r = e / SBLK, cc = e % SBLK;
         outT[r * SBLK + cc] = (cc < nb && r < nb && r >= cc) ? Cs[cc * LDI + r] : 0.0;    // DinvT (column r, row cc) = X[r, cc]
     }
+    // transposed copy of the sub-diagonal tile L[(bi+1) block rows, bi block cols] for the backward sweep:
+    // LsubT[b][rr * 128 + cc] = L[lc0 + 128 + rr, lc0 + cc]
+    __syncthreads();                                         // Cs is reused as the transposition buffer
+    double* sub = c.LsubT + (int64_t)b * SBLK * SBLK;
+    const int32_t nbn = min(SBLK, nc - (lc0 + SBLK));       // rows of the next diagonal block (<= 0: none)
+    const double* Lsub = c.Lx + c.sn_xptr[s] + (int64_t)lc0 * ld + lc0 + SBLK;
+    for (int cc = 0; cc < SBLK; ++cc) {
+        const int rr = tid;                                  // coalesced read along the rows
+        Cs[cc * LDI + rr] = (rr < nbn && cc < nb) ? Lsub[(int64_t)cc * ld + rr] : 0.0;
+    }
+    __syncthreads();
+    for (int e = tid; e < SBLK * SBLK; e += INV_THREADS) {
+        const int rr = e / SBLK, cc = e % SBLK;
+        sub[rr * SBLK + cc] = Cs[cc * LDI + rr];
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -324,6 +339,7 @@ __global__ void __launch_bounds__(SL_THREADS, 1) k_fwd_large(DevCtx c, int32_t b
         }
         double t[32];
         double acc = 0.0;
+        const double bown = (I.kind == 0 && tid < SBLK && rvalid) ? __ldcg(c.wk + f + I.r0 + tid) : 0.0;   // off the chain
         auto load_tile = [&](int j) {
             const int32_t nbj = min(SBLK, nc - j * SBLK);
             const double* col = panel + (int64_t)(j * SBLK + cg * 32) * ld + prow;
@@ -351,7 +367,7 @@ __global__ void __launch_bounds__(SL_THREADS, 1) k_fwd_large(DevCtx c, int32_t b
             continue;
         }
         if (tid < SBLK)
-            xs[tid] = rvalid ? (__ldcg(c.wk + f + I.r0 + tid) + red[tid] + red[SBLK + tid] + red[2 * SBLK + tid] + red[3 * SBLK + tid]) : 0.0;
+            xs[tid] = rvalid ? (bown + red[tid] + red[SBLK + tid] + red[2 * SBLK + tid] + red[3 * SBLK + tid]) : 0.0;
         cp_async_wait_all();
         __syncthreads();
         double a2 = 0.0;
@@ -393,6 +409,12 @@ __global__ void __launch_bounds__(SL_THREADS, 1) k_bwd_large(DevCtx c, int32_t b
             for (int e = tid; e < SBLK * SBLK / 2; e += SL_THREADS) cp_async16(Ds + 2 * e, src + 2 * e);
             cp_async_commit();
         }
+        // own right-hand side and signs: off the critical chain
+        double bown = 0.0, sown = 1.0;
+        if (tid < SBLK && tid < I.nr) {
+            bown = __ldcg(c.wk + f + i * SBLK + tid);
+            sown = (double)c.sign[f + i * SBLK + tid];
+        }
         // p[cc] accumulates sum_r L[r, i*128 + cg*32 + cc] * x[r] over this thread's rows r (mod 128)
         double p[32];
 #pragma unroll
@@ -409,8 +431,8 @@ __global__ void __launch_bounds__(SL_THREADS, 1) k_bwd_large(DevCtx c, int32_t b
                     if (cc < ncv) p[cc] += colbase[(int64_t)cc * ld + rr] * xr;
             }
         }
-        // later diagonal blocks of the same supernode, nearest last (it is the one we wait for)
-        for (int32_t j = ncb - 1; j > i; --j) {
+        // later diagonal blocks except the adjacent one: their x has been available for a while
+        for (int32_t j = ncb - 1; j > i + 1; --j) {
             wait_flag(bflag + db + j);
             const int32_t rr = j * SBLK + r;
             if (rr < nc) {
@@ -434,9 +456,28 @@ __global__ void __launch_bounds__(SL_THREADS, 1) k_bwd_large(DevCtx c, int32_t b
         __syncthreads();
         red[wq * SBLK + cg * 32 + lane] = p[0];          // 4 warps (row quarters) per column group
         __syncthreads();
-        if (tid < SBLK)
-            xs[tid] = (tid < I.nr) ? ((double)c.sign[f + i * SBLK + tid] * __ldcg(c.wk + f + i * SBLK + tid)
-                                      - (red[tid] + red[SBLK + tid] + red[2 * SBLK + tid] + red[3 * SBLK + tid])) : 0.0;
+        double part = 0.0;                               // thread tid < 128 owns column tid of block i
+        if (tid < SBLK) part = red[tid] + red[SBLK + tid] + red[2 * SBLK + tid] + red[3 * SBLK + tid];
+        // the adjacent block (i+1) is the one on the critical chain: its tile was stored transposed at
+        // factorisation time, so it can be prefetched into registers before the wait and applied row-wise
+        if (i + 1 < ncb) {
+            const double* T = c.LsubT + (int64_t)(db + i) * SBLK * SBLK;
+            double t[32];
+#pragma unroll
+            for (int cc = 0; cc < 32; ++cc) t[cc] = T[(cg * 32 + cc) * SBLK + r];
+            wait_flag(bflag + db + i + 1);
+            if (tid < SBLK) xs[tid] = ((i + 1) * SBLK + tid < nc) ? __ldcg(c.wk + f + (i + 1) * SBLK + tid) : 0.0;
+            __syncthreads();
+            double a1 = 0.0;
+#pragma unroll
+            for (int cc = 0; cc < 32; ++cc) a1 += t[cc] * xs[cg * 32 + cc];
+            __syncthreads();
+            red[cg * SBLK + r] = a1;
+            __syncthreads();
+            if (tid < SBLK) part += red[tid] + red[SBLK + tid] + red[2 * SBLK + tid] + red[3 * SBLK + tid];
+            __syncthreads();
+        }
+        if (tid < SBLK) xs[tid] = (tid < I.nr) ? (sown * bown - part) : 0.0;
         cp_async_wait_all();
         __syncthreads();
         // x = X' * tmp : row r of X' is column r of X; Ds holds X' column-major -> Ds[col*128 + row]

@@ -38,6 +38,7 @@ struct DevCtx {
     double* Lx;
     double* Dinv;    // [ndblk][128*128] explicit inverses of the diagonal blocks (column-major, lower)
     double* DinvT;   // [ndblk][128*128] their transposes (column-major, upper)
+    double* LsubT;   // [ndblk][128*128] transposed sub-diagonal tile of each diagonal block (backward sweep)
     int32_t* flags;  // [2*ndblk] forward / backward "block solved" flags of the dense solve kernels
     int32_t* info;   // info[0] = smallest permuted column with a bad pivot (INT_MAX if none)
     double* wk;      // [N] work vector of the triangular solves (permuted order)

@@ -499,6 +499,7 @@ void setup_device(tlpb200_solver* s) {
     c.Lx = dalloc<double>(s, (size_t)S.lx_size);
     c.Dinv = dalloc<double>(s, (size_t)P.ndblk * SBLK * SBLK);
     c.DinvT = dalloc<double>(s, (size_t)P.ndblk * SBLK * SBLK);
+    c.LsubT = dalloc<double>(s, (size_t)P.ndblk * SBLK * SBLK);
     c.flags = dalloc<int32_t>(s, (size_t)2 * P.ndblk);
     c.info = dalloc<int32_t>(s, 4);
     c.wk = dalloc<double>(s, (size_t)S.N);
