@@ -269,8 +269,8 @@ def gpu_arm(args):
                 "launches_per_step": int(n_upd), "avg_launch_ms": round(ms_upd / max(1, n_upd), 4),
                 "algorithmic_flops_per_step": flops_upd, "share_of_update_ms": round(ms_upd / max(1e-9, sp["ms_assemble"] + sp["ms_factor"]), 3)}
     solve_bytes = 16.0 * sp["nnzL_stored"] if sp["nnzL_stored"] else 0.0
-    ms_tri = sum(cls[k][0] for k in ("fwd_small", "fwd_large", "bwd_large", "bwd_small"))
-    roofline_solve = {"kernel": "supernodal forward+backward sweep (one rhs)", "bound": "hbm",
+    ms_tri = sum(cls[k][0] for k in ("fwd_small", "fwd_large", "bwd_large", "bwd_small", "fwd_big", "bwd_big"))
+    roofline_solve = {"kernel": "supernodal forward+backward sweep (one rhs): k_fwd_big + k_bwd_big (+ small/medium supernode kernels)", "bound": "hbm",
                       "achieved": round(16.0 * sp["nnzL"] / (ms_tri * 1e-3) / 1e9, 1) if ms_tri > 0 else None,
                       "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                       "frac": round(16.0 * sp["nnzL"] / (ms_tri * 1e-3) / 1e9 / peaks["hbm_gbs"], 4) if ms_tri > 0 else None,

@@ -52,7 +52,9 @@ typedef struct tlpb200_options {
     int32_t rank, nranks;  /* multi-GPU subtree sharding: this process's rank and the world size (default 0, 1) */
     int32_t dense_col_threshold; /* K1: columns with more non-zeros are handled by a low-rank Schur correction;
                                     0 = auto (max(32, 5% of m)), < 0 = off */
-    int32_t reserved[6];
+    int32_t dense_solve_ncol;    /* non-small supernodes with at least this many columns use the dense-solve path
+                                    (repacked unit-block-diagonal tiles, flag-in-data hand-over); 0 = default (384) */
+    int32_t reserved[5];
 } tlpb200_options;
 
 typedef struct tlpb200_stats {
@@ -123,6 +125,11 @@ int tlpb200_get_structure(const tlpb200_solver* s, int64_t* rowptr, int32_t* row
  * tlpb200_debug_assemble call, the assembled matrix) back to the host: Lx[nnzL_stored]. */
 int tlpb200_debug_assemble(tlpb200_solver* s, const double* theta_inv, const double* regP, const double* regD);
 int tlpb200_debug_get_lx(tlpb200_solver* s, double* lx, int64_t* xptr /* nsuper+1, may be NULL */);
+/* dense-solve plan of the big supernodes (host data; works on analyze_only handles): counts[6] = #pack tasks,
+   #forward tasks, #backward tasks, #forward tiles, #backward tiles, #exchange slots; the arrays receive the raw
+   32-byte pack records {i32 sn, r0, nr, j; i64 fdst, bdst} and 40-byte task records
+   {i32 sn, kind, blk, r0, nr, ntile, nbelow, xq0; i64 tile0}.  Any pointer may be NULL. */
+int tlpb200_debug_big_plan(const tlpb200_solver* s, int64_t* counts, void* pack, void* fwd, void* bwd);
 
 /* ---- multi-GPU, one process per GPU (no counterpart in the reference, NEWS.md:31) -------------
  * Created with opt.nranks > 1 every rank analyses the same matrix, owns the elimination-tree subtrees

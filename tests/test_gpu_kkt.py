@@ -127,6 +127,51 @@ def test_solve_parity_vs_oracle(cfg, sysname):
         assert ex <= max(1e-8, 100 * sx) and ey <= max(1e-8, 100 * sy), (ex, ey, sx, sy)
 
 
+DENSE_SOLVE_CASES = [
+    ("cfg2-mini", lambda: lpgen.config(2, mini=True), "K1", 1),
+    ("cfg4-mini", lambda: lpgen.config(4, mini=True), "K1", 1),
+    ("staircase-K2", lambda: lpgen.staircase(stages=8, nodes=150, arcs=260, name="st"), "K2", 1),
+    ("random-700", lambda: lpgen.random_sparse(700, 1400, 6, name="r700"), "K1", 1),
+    ("random-400-K2", lambda: lpgen.random_sparse(400, 800, 5, name="r400"), "K2", 200),
+    ("block-angular", lambda: lpgen.block_angular(blocks=3, mb=300, nb=600, width=64, link=150, name="ba"), "K1", 130),
+    ("random-2000", lambda: lpgen.random_sparse(2000, 4000, 8, name="r2000"), "K1", 0),   # default threshold: root only
+]
+
+
+@pytest.mark.parametrize("name,gen,sysname,ncol", DENSE_SOLVE_CASES, ids=[c[0] for c in DENSE_SOLVE_CASES])
+def test_dense_solve_path_parity(name, gen, sysname, ncol):
+    """The dense-solve path (repacked unit-block-diagonal tiles, flag-in-data hand-over; ragged edge blocks, rows
+    below the columns, K2 signs) against the oracle and against the block path on the same factor."""
+    lp = gen()
+    A = lp.A
+    m, n = A.shape
+    rng = np.random.default_rng(11)
+    kd = pkg.setup(A, SYSTEMS[sysname](), pkg.Backend(dense_solve_ncol=ncol))
+    kb = pkg.setup(A, SYSTEMS[sysname](), pkg.Backend(dense_solve_ncol=10 ** 9))
+    assert len(kd.big_plan()["fwd"]) > 0 and len(kb.big_plan()["fwd"]) == 0
+    o = _oracle(A, sysname)
+    for rep in range(3):                                  # repeated sweeps: the exchange slots are reused with a new key
+        theta = np.exp(rng.uniform(-2, 2, n)); regP = np.full(n, 1e-4); regD = np.full(m, 1e-4)
+        xi_p = rng.standard_normal(m); xi_d = rng.standard_normal(n)
+        for k in (kd, kb, o):
+            k.update(theta, regP, regD)
+        sols = []
+        for k in (kd, kb, o):
+            dx = np.zeros(n); dy = np.zeros(m)
+            k.solve(dx, dy, xi_p, xi_d)
+            if k is kd:                                   # same rhs twice on the same factor: bitwise-stable hand-over
+                dx2 = np.zeros(n); dy2 = np.zeros(m)
+                k.solve(dx2, dy2, xi_p, xi_d)
+                assert np.allclose(dx2, dx, rtol=1e-12, atol=1e-12 * np.abs(dx).max())
+                assert np.allclose(dy2, dy, rtol=1e-12, atol=1e-12 * np.abs(dy).max())
+            sols.append(np.concatenate([dx, dy]))
+        ref = np.abs(sols[2]).max()
+        assert np.abs(sols[0] - sols[2]).max() / ref < 1e-8, np.abs(sols[0] - sols[2]).max() / ref
+        assert np.abs(sols[0] - sols[1]).max() / ref < 1e-9, np.abs(sols[0] - sols[1]).max() / ref
+        rp, rd = kkt_ref.kkt_residuals(A, theta, regP, regD, sols[0][:n], sols[0][n:], xi_p, xi_d)
+        assert rp <= SQRT_EPS * max(1.0, ref) and rd <= SQRT_EPS * max(1.0, ref)
+
+
 def test_errors_match_reference():
     A = lpgen.config(2, mini=True).A
     m, n = A.shape

@@ -21,7 +21,8 @@ class Options(C.Structure):
     _fields_ = [("ordering", C.c_int32), ("device", C.c_int32), ("piece_width", C.c_int32),
                 ("small_elems", C.c_int32), ("relax_always", C.c_int32), ("use_graph", C.c_int32),
                 ("analyze_only", C.c_int32), ("rank", C.c_int32), ("nranks", C.c_int32),
-                ("dense_col_threshold", C.c_int32), ("reserved", C.c_int32 * 6)]
+                ("dense_col_threshold", C.c_int32), ("dense_solve_ncol", C.c_int32),
+                ("reserved", C.c_int32 * 5)]
 
 
 class Stats(C.Structure):
@@ -46,7 +47,8 @@ class Stats(C.Structure):
 
 
 KERNEL_CLASSES = ["assemble", "small_factor", "diag_factor", "trsm", "update", "rhs_recover",
-                  "fwd_small", "fwd_large", "update128", "bwd_large", "invert_diag", "bwd_small", "dense_cols"]
+                  "fwd_small", "fwd_large", "update128", "bwd_large", "invert_diag", "bwd_small", "dense_cols",
+                  "pack_big", "fwd_big", "bwd_big"]
 
 
 # every symbol include/tlpb200.h declares (tests check that the library exports all of them)
@@ -58,7 +60,7 @@ SYMBOLS = [
     "tlpb200_backend_name", "tlpb200_linear_system", "tlpb200_destroy",
     "tlpb200_dist_info", "tlpb200_update_begin", "tlpb200_top_panels", "tlpb200_update_end",
     "tlpb200_solve_begin", "tlpb200_work_vector", "tlpb200_solve_mid", "tlpb200_solve_end",
-    "tlpb200_get_dense_cols",
+    "tlpb200_get_dense_cols", "tlpb200_debug_big_plan",
 ]
 
 _lib = None
@@ -106,6 +108,8 @@ def load():
         getattr(lib, name).restype = C.c_int
     lib.tlpb200_get_dense_cols.argtypes = [p, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]
     lib.tlpb200_get_dense_cols.restype = C.c_int
+    lib.tlpb200_debug_big_plan.argtypes = [p, C.POINTER(C.c_int64), p, p, p]
+    lib.tlpb200_debug_big_plan.restype = C.c_int
     lib.tlpb200_last_error.argtypes = [p]
     lib.tlpb200_last_error.restype = C.c_char_p
     lib.tlpb200_backend_name.argtypes = []

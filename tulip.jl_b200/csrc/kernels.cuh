@@ -45,6 +45,14 @@ struct DevCtx {
     int32_t N;
     int32_t ndblk;
     int32_t has_neg;   // 1 when some pivots are expected negative (K2)
+    // dense-solve path of the big supernodes (kernels_dense_solve.cu)
+    const BigPack* big_pack;
+    const BigTask* fwd_big;
+    const BigTask* bwd_big;
+    double* Ft;                    // forward tiles  (column-major 128x128, contiguous)
+    double* Bt;                    // backward tiles (row-major 128x128, contiguous)
+    unsigned long long* xq;        // exchange slots: {bits(x), bits(x) ^ key(epoch)} per entry
+    unsigned long long* epoch;     // [0] sweep counter (bumped by the last CTA of every dense sweep), [1] exit counter
     const int8_t* skip;   // multi-GPU: skip[s] != 0 -> supernode s is not processed in this phase on this rank (nullptr: none)
 };
 
@@ -102,6 +110,11 @@ void launch_fwd_small(const DevCtx& c, int32_t begin, int32_t end, cudaStream_t 
 void launch_bwd_small(const DevCtx& c, int32_t begin, int32_t end, cudaStream_t st);
 void launch_fwd_large(const DevCtx& c, int32_t begin, int32_t end, int nsm, cudaStream_t st);
 void launch_bwd_large(const DevCtx& c, int32_t begin, int32_t end, int nsm, cudaStream_t st);
+
+void launch_pack_big(const DevCtx& c, int32_t begin, int32_t end, cudaStream_t st);
+void launch_fwd_big(const DevCtx& c, int32_t begin, int32_t end, int nsm, cudaStream_t st);
+void launch_bwd_big(const DevCtx& c, int32_t begin, int32_t end, int nsm, cudaStream_t st);
+cudaError_t dense_solve_static_init();
 
 void launch_zero_unowned(const DevCtx& c, const int8_t* keep, cudaStream_t st);   // wk[q] = 0 where keep[q] == 0
 void launch_k1_rhs(const DevCtx& c, const DevMat& A, const double* d, const double* xi_p, const double* xi_d,

@@ -54,6 +54,12 @@ void build_plan(const Symbolic& S, const PlanOptions& opt, Plan& P) {
     P.sn_small.assign(ns, 0);
     P.sn_level.assign(ns, 0);
     P.sn_dblk.assign(ns, -1);
+    P.sn_big.assign(ns, 0);
+    P.big_pack.clear();
+    P.fwd_big.clear();
+    P.bwd_big.clear();
+    P.n_ftiles = P.n_btiles = 0;
+    P.xq_slots = 0;
     P.dblk_sn.clear();
     P.dblk_idx.clear();
     P.seg_ptr.assign(ns + 1, 0);
@@ -89,6 +95,7 @@ void build_plan(const Symbolic& S, const PlanOptions& opt, Plan& P) {
             P.max_small_nrow = std::max(P.max_small_nrow, nr);
         } else {
             const int32_t np = (nc + PIECE - 1) / PIECE;
+            if (nc >= opt.big_ncol) P.sn_big[s] = 1;
             P.sn_dblk[s] = (int32_t)P.dblk_sn.size();
             for (int32_t k = 0; k < np; ++k) {
                 Piece pc;
@@ -116,9 +123,10 @@ void build_plan(const Symbolic& S, const PlanOptions& opt, Plan& P) {
         for (int32_t j = S.sn_first[s]; j < S.sn_first[s + 1]; ++j)
             col_level[j] = P.sn_small[s] ? P.sn_level[s] : base_level[s] + (j - S.sn_first[s]) / PIECE;
 
-    std::vector<std::vector<int32_t>> lsmall(nlev), lpiece(nlev), llarge(nlev);
+    std::vector<std::vector<int32_t>> lsmall(nlev), lpiece(nlev), llarge(nlev), lbig(nlev);
     for (int32_t s = 0; s < ns; ++s) {
         if (P.sn_small[s]) lsmall[P.sn_level[s]].push_back(s);
+        else if (P.sn_big[s]) lbig[base_level[s]].push_back(s);
         else llarge[base_level[s]].push_back(s);
     }
     for (int32_t p = 0; p < (int32_t)P.pieces.size(); ++p) lpiece[P.pieces[p].level].push_back(p);
@@ -241,6 +249,81 @@ void build_plan(const Symbolic& S, const PlanOptions& opt, Plan& P) {
         }
         lp.fwd_end = (int32_t)P.fwd_items.size();
         lp.bwd_end = (int32_t)P.bwd_items.size();
+
+        // dense-solve tasks of the big supernodes that start at this level: same wavefront order; the tiles
+        // of a task are laid out contiguously in the order the task streams them
+        lp.fbig_begin = (int32_t)P.fwd_big.size();
+        lp.bbig_begin = (int32_t)P.bwd_big.size();
+        if (!lbig[L].empty()) {
+            const size_t nb_ = lbig[L].size();
+            std::vector<int32_t> xq0(nb_);
+            std::vector<std::vector<int64_t>> ftile0(nb_), btile0(nb_);   // per supernode: first tile of every fwd / bwd task
+            int32_t maxblk = 0, maxcb = 0;
+            for (size_t x = 0; x < nb_; ++x) {
+                const int32_t s = lbig[L][x];
+                const int32_t nc = sn_ncol(S, s), nr = sn_nrow(S, s);
+                const int32_t ncb = (nc + SBLK - 1) / SBLK, nbb = (nr - nc + SBLK - 1) / SBLK;
+                maxblk = std::max(maxblk, ncb + nbb);
+                maxcb = std::max(maxcb, ncb);
+                xq0[x] = P.xq_slots;
+                P.xq_slots += ncb * SBLK;
+                ftile0[x].resize(ncb + nbb);
+                btile0[x].resize(ncb);
+                for (int32_t b = 0; b < ncb + nbb; ++b) { ftile0[x][b] = P.n_ftiles; P.n_ftiles += (b < ncb) ? b : ncb; }
+                for (int32_t k = 0; k < ncb; ++k) { btile0[x][k] = P.n_btiles; P.n_btiles += nbb + (ncb - 1 - k); }
+                // one pack task per tile: block row b (column block or below block) x column block j
+                for (int32_t b = 0; b < ncb + nbb; ++b) {
+                    const int32_t rr0 = (b < ncb) ? b * SBLK : nc + (b - ncb) * SBLK;   // below blocks start at row nc
+                    const int32_t rnr = (b < ncb) ? std::min(SBLK, nc - rr0) : std::min(SBLK, nr - rr0);
+                    const int32_t nj = (b < ncb) ? b : ncb;
+                    for (int32_t j = 0; j < nj; ++j) {
+                        BigPack pk;
+                        pk.sn = s;
+                        pk.r0 = rr0;
+                        pk.nr = rnr;
+                        pk.j = j;
+                        pk.fdst = ftile0[x][b] + j;
+                        pk.bdst = btile0[x][j] + ((b < ncb) ? nbb + (ncb - 1 - b) : (b - ncb));
+                        P.big_pack.push_back(pk);
+                    }
+                }
+            }
+            for (int32_t b = 0; b < maxblk; ++b)
+                for (size_t x = 0; x < nb_; ++x) {
+                    const int32_t s = lbig[L][x];
+                    const int32_t nc = sn_ncol(S, s), nr = sn_nrow(S, s);
+                    const int32_t ncb = (nc + SBLK - 1) / SBLK, nbb = (nr - nc + SBLK - 1) / SBLK;
+                    if (b >= ncb + nbb) continue;
+                    BigTask t;
+                    t.sn = s;
+                    t.nbelow = 0;
+                    t.xq0 = xq0[x];
+                    t.tile0 = ftile0[x][b];
+                    if (b < ncb) { t.kind = 0; t.blk = b; t.r0 = b * SBLK; t.nr = std::min(SBLK, nc - t.r0); t.ntile = b; }
+                    else { t.kind = 1; t.blk = b - ncb; t.r0 = nc + (b - ncb) * SBLK; t.nr = std::min(SBLK, nr - t.r0); t.ntile = ncb; }
+                    P.fwd_big.push_back(t);
+                }
+            for (int32_t d = 0; d < maxcb; ++d)
+                for (size_t x = 0; x < nb_; ++x) {
+                    const int32_t s = lbig[L][x];
+                    const int32_t nc = sn_ncol(S, s), nr = sn_nrow(S, s);
+                    const int32_t ncb = (nc + SBLK - 1) / SBLK, nbb = (nr - nc + SBLK - 1) / SBLK;
+                    if (d >= ncb) continue;
+                    BigTask t;
+                    t.sn = s;
+                    t.kind = 0;
+                    t.blk = ncb - 1 - d;
+                    t.r0 = t.blk * SBLK;
+                    t.nr = std::min(SBLK, nc - t.r0);
+                    t.nbelow = nbb;
+                    t.ntile = nbb + d;
+                    t.xq0 = xq0[x];
+                    t.tile0 = btile0[x][t.blk];
+                    P.bwd_big.push_back(t);
+                }
+        }
+        lp.fbig_end = (int32_t)P.fwd_big.size();
+        lp.bbig_end = (int32_t)P.bwd_big.size();
     }
 }
 

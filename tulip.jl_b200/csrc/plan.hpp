@@ -19,6 +19,7 @@ struct PlanOptions {
     int small_elems = 4096;   // supernodes with nrow*ncol <= small_elems, ncol <= small_ncol and
     int small_ncol = 32;      // nrow <= small_nrow run in the one-CTA kernels
     int small_nrow = 256;
+    int big_ncol = 384;       // non-small supernodes with >= big_ncol columns use the dense-solve path (BigTask)
 };
 
 // One column piece [c0,c1) of supernode sn (global permuted column indices), c1-c0 <= PIECE.
@@ -51,6 +52,31 @@ struct SolveItem {
     int32_t pad;
 };
 
+// ---- dense-solve ("big") supernodes -------------------------------------------------------------
+// After the factorisation the panel of a big supernode is repacked into 128x128 tiles of
+// Lhat = L * blockdiag(L_kk)^{-1} (unit block diagonal), each tile contiguous (16384 doubles, zero padded):
+//   Ft: tile (I, j) column-major   [c*128 + r] = Lhat[I.r0 + r, j*128 + c]   (forward sweep, block row I)
+//   Bt: the same tile row-major    [r*128 + c]                               (backward sweep, block column j)
+// The tiles of one solve task are contiguous in the order the task streams them.
+struct BigPack {
+    int32_t sn;
+    int32_t r0, nr;   // row range of the tile inside the supernode's row list
+    int32_t j;        // column block
+    int64_t fdst;     // tile index inside Ft
+    int64_t bdst;     // tile index inside Bt
+};
+
+struct BigTask {
+    int32_t sn;
+    int32_t kind;     // forward: 0 = block row inside the columns, 1 = block of rows below.  backward: 0
+    int32_t blk;      // column block (kind 0) / below block (kind 1)
+    int32_t r0, nr;   // row range inside the supernode's row list
+    int32_t ntile;    // tiles streamed: forward kind 0: blk, kind 1: ncb; backward: nbelow + (ncb-1-blk)
+    int32_t nbelow;   // backward: leading tiles whose x is gathered from wk through the row list
+    int32_t xq0;      // first exchange slot of the supernode (slot = xq0 + column offset inside the supernode)
+    int64_t tile0;    // first tile inside Ft / Bt
+};
+
 struct LevelPlan {
     int32_t small_begin = 0, small_end = 0;    // Plan::small_list
     int32_t piece_begin = 0, piece_end = 0;    // Plan::level_pieces (diag-factor CTAs)
@@ -61,6 +87,8 @@ struct LevelPlan {
     int32_t ext_atomic = 1;
     int32_t fwd_begin = 0, fwd_end = 0;        // Plan::fwd_items (supernodes whose first piece is at this level)
     int32_t bwd_begin = 0, bwd_end = 0;        // Plan::bwd_items
+    int32_t fbig_begin = 0, fbig_end = 0;      // Plan::fwd_big (big supernodes that start at this level)
+    int32_t bbig_begin = 0, bbig_end = 0;      // Plan::bwd_big
 };
 
 struct Plan {
@@ -81,6 +109,11 @@ struct Plan {
     std::vector<UpdTask> upd128;
     std::vector<PanelTask> panel;
     std::vector<SolveItem> fwd_items, bwd_items;
+    std::vector<int32_t> sn_big;          // [nsuper] 1 = dense-solve path
+    std::vector<BigPack> big_pack;
+    std::vector<BigTask> fwd_big, bwd_big;
+    int64_t n_ftiles = 0, n_btiles = 0;   // tiles of Ft / Bt
+    int32_t xq_slots = 0;                 // exchange slots (sum over big supernodes of ncb*128)
     std::vector<LevelPlan> levels;
     int32_t max_small_elems = 0;          // largest nrow*ncol among small supernodes
     int32_t max_small_nrow = 0;

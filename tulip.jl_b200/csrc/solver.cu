@@ -139,7 +139,7 @@ struct Scope {
 
 void collect_profile(tlpb200_solver* s, bool reset_update_classes) {
     // called after a stream sync
-    static const bool is_update_class[16] = {1, 1, 1, 1, 1, 0, 0, 0, 1, 0, 1, 0, 0, 0, 0, 0};   // class 12 (dense cols) is left cumulative
+    static const bool is_update_class[16] = {1, 1, 1, 1, 1, 0, 0, 0, 1, 0, 1, 0, 0, 1, 0, 0};   // class 12 (dense cols) is left cumulative
     for (int c = 0; c < 16; ++c)
         if (is_update_class[c] == reset_update_classes) { s->ms_class[c] = 0; s->n_class[c] = 0; }
     for (size_t i = 0; i + 1 < s->pool_used; i += 2) {
@@ -237,6 +237,7 @@ void enqueue_factor(tlpb200_solver* s, int64_t& count) {
     }
     if (overlap && last_lazy > waited) CK(cudaStreamWaitEvent(st, s->ev_lazy[last_lazy], 0));   // join
     if ((*s->cur).ndblk > 0) { Scope sc(s, 10); launch_invert_diag((*s->cur), st); count++; }
+    if (!s->plan.big_pack.empty()) { Scope sc(s, 13); launch_pack_big((*s->cur), 0, (int32_t)s->plan.big_pack.size(), st); count++; }
     if (s->dc.nd > 0) {
         // V = K_s^{-1} A_d : one sparse solve per dense column, then the nd x nd Schur matrix and its Cholesky factor
         Scope sc(s, 12);
@@ -273,6 +274,7 @@ void enqueue_fwd(tlpb200_solver* s, int64_t& count) {
         const LevelPlan& lp = L[l];
         if (lp.small_end > lp.small_begin) { Scope sc(s, 6); launch_fwd_small((*s->cur), lp.small_begin, lp.small_end, st); count++; }
         if (lp.fwd_end > lp.fwd_begin) { Scope sc(s, 7); launch_fwd_large((*s->cur), lp.fwd_begin, lp.fwd_end, s->nsm, st); count++; }
+        if (lp.fbig_end > lp.fbig_begin) { Scope sc(s, 14); launch_fwd_big((*s->cur), lp.fbig_begin, lp.fbig_end, s->nsm, st); count++; }
     }
 }
 
@@ -281,6 +283,7 @@ void enqueue_bwd(tlpb200_solver* s, int64_t& count) {
     const auto& L = s->plan.levels;
     for (size_t l = L.size(); l-- > 0;) {
         const LevelPlan& lp = L[l];
+        if (lp.bbig_end > lp.bbig_begin) { Scope sc(s, 15); launch_bwd_big((*s->cur), lp.bbig_begin, lp.bbig_end, s->nsm, st); count++; }
         if (lp.bwd_end > lp.bwd_begin) { Scope sc(s, 9); launch_bwd_large((*s->cur), lp.bwd_begin, lp.bwd_end, s->nsm, st); count++; }
         if (lp.small_end > lp.small_begin) { Scope sc(s, 11); launch_bwd_small((*s->cur), lp.small_begin, lp.small_end, st); count++; }
     }
@@ -378,7 +381,7 @@ void run_update(tlpb200_solver* s) {
         enqueue_factor(s, cnt);
         s->launches_update = cnt;
     }
-    CK(cudaMemcpyAsync(s->h_info, s->ctx.info, sizeof(int32_t), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaMemcpyAsync(s->h_info, s->ctx.info, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, s->stream));
     s->n_update++;
 }
 
@@ -393,6 +396,8 @@ int finish_update(tlpb200_solver* s, int64_t* bad_pivot) {
         collect_profile(s, true);
     }
     const int32_t info = *s->h_info;
+    if (s->h_info[2] != 0)
+        return fail(s, TLPB200_INTERNAL, "dense-solve hand-over timed out in an earlier solve (exchange slot never published)");
     s->bad_pivot = (info >= 0 && info < s->sym.N) ? info : -1;
     if (bad_pivot) *bad_pivot = s->bad_pivot;
     if (s->bad_pivot >= 0) {
@@ -464,6 +469,7 @@ void setup_device(tlpb200_solver* s) {
     }
     s->stream = s->own_stream;
     CK(kernels_static_init());
+    CK(dense_solve_static_init());
     for (auto& ev : s->ev) CK(cudaEventCreate(&ev));
 
     const Symbolic& S = s->sym;
@@ -502,6 +508,16 @@ void setup_device(tlpb200_solver* s) {
     c.LsubT = dalloc<double>(s, (size_t)P.ndblk * SBLK * SBLK);
     c.flags = dalloc<int32_t>(s, (size_t)2 * P.ndblk);
     c.info = dalloc<int32_t>(s, 4);
+    CK(cudaMemset(c.info, 0, 4 * sizeof(int32_t)));
+    c.big_pack = upload(s, P.big_pack);
+    c.fwd_big = upload(s, P.fwd_big);
+    c.bwd_big = upload(s, P.bwd_big);
+    c.Ft = dalloc<double>(s, (size_t)P.n_ftiles * SBLK * SBLK);
+    c.Bt = dalloc<double>(s, (size_t)P.n_btiles * SBLK * SBLK);
+    c.xq = dalloc<unsigned long long>(s, (size_t)2 * P.xq_slots);
+    CK(cudaMemset(c.xq, 0, std::max<size_t>(2 * (size_t)P.xq_slots, 1) * sizeof(unsigned long long)));
+    c.epoch = dalloc<unsigned long long>(s, 2);
+    CK(cudaMemset(c.epoch, 0, 2 * sizeof(unsigned long long)));
     c.wk = dalloc<double>(s, (size_t)S.N);
     CK(cudaMemset(c.wk, 0, std::max<size_t>(S.N, 1) * sizeof(double)));
     c.skip = nullptr;
@@ -670,6 +686,8 @@ int tlpb200_create(tlpb200_solver** out, int64_t m, int64_t n, const int64_t* co
         if (s->nranks > 1) s->top_begin = relayout_panels(s->sym, s->owner);
         PlanOptions po;
         po.small_elems = s->opt.small_elems;
+        if (s->opt.dense_solve_ncol > 0) po.big_ncol = s->opt.dense_solve_ncol;
+        if (const char* e = getenv("TLPB200_DENSE_SOLVE_NCOL")) po.big_ncol = std::max(1, atoi(e));
         build_plan(s->sym, po, s->plan);
         if (system == TLPB200_K1)
             build_assembly_k1(s->sym, m, n, cp_f, ri_f, va_f, s->maps);
@@ -895,6 +913,23 @@ int tlpb200_debug_get_lx(tlpb200_solver* s, double* lx, int64_t* xptr) {
     }
 }
 
+int tlpb200_debug_big_plan(const tlpb200_solver* s, int64_t* counts, void* pack, void* fwd, void* bwd) {
+    if (!s) return TLPB200_BAD_ARG;
+    const Plan& P = s->plan;
+    if (counts) {
+        counts[0] = (int64_t)P.big_pack.size();
+        counts[1] = (int64_t)P.fwd_big.size();
+        counts[2] = (int64_t)P.bwd_big.size();
+        counts[3] = P.n_ftiles;
+        counts[4] = P.n_btiles;
+        counts[5] = P.xq_slots;
+    }
+    if (pack && !P.big_pack.empty()) std::memcpy(pack, P.big_pack.data(), P.big_pack.size() * sizeof(BigPack));
+    if (fwd && !P.fwd_big.empty()) std::memcpy(fwd, P.fwd_big.data(), P.fwd_big.size() * sizeof(BigTask));
+    if (bwd && !P.bwd_big.empty()) std::memcpy(bwd, P.bwd_big.data(), P.bwd_big.size() * sizeof(BigTask));
+    return TLPB200_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Multi-GPU (one process per GPU): subtree-sharded factorisation.  The caller (tulip.jl_b200/parallel.py,
 // torch.distributed / NCCL) performs the collectives between the phases on the exposed device buffers.
@@ -957,7 +992,7 @@ int tlpb200_update_end(tlpb200_solver* s, int64_t* bad_pivot) {
         enqueue_factor(s, cnt);
         s->cur = &s->ctx;
         s->launches_update += cnt;
-        CK(cudaMemcpyAsync(s->h_info, s->ctx.info, sizeof(int32_t), cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaMemcpyAsync(s->h_info, s->ctx.info, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, s->stream));
         s->n_update++;
         return finish_update(s, bad_pivot);
     } catch (const CudaFail& f) {

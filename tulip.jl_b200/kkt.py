@@ -49,6 +49,7 @@ class Backend:
     rank: int = 0               # multi-GPU subtree sharding (tulip.jl_b200/parallel.py sets these)
     nranks: int = 1
     dense_col_threshold: int = 0  # K1 dense-column Schur path: 0 auto (max(32, 5% of m)), < 0 off
+    dense_solve_ncol: int = 0     # supernodes with >= this many columns use the dense-solve path (0 = default 384)
 
 
 # ---- exceptions (what the reference throws at this boundary) ---------------------------------
@@ -113,6 +114,7 @@ class B200KKTSolver:
         opt.rank = backend.rank
         opt.nranks = backend.nranks
         opt.dense_col_threshold = backend.dense_col_threshold
+        opt.dense_solve_ncol = backend.dense_solve_ncol
         colptr = np.ascontiguousarray(A.indptr, dtype=np.int64)
         rowval = np.ascontiguousarray(A.indices, dtype=np.int64)
         nzval = np.ascontiguousarray(A.data, dtype=np.float64)
@@ -267,6 +269,24 @@ class B200KKTSolver:
         if rc != _lib.OK:
             _raise(rc, self._h)
         return lx, xptr
+
+
+    PACK_DTYPE = np.dtype([("sn", "<i4"), ("r0", "<i4"), ("nr", "<i4"), ("j", "<i4"), ("fdst", "<i8"), ("bdst", "<i8")])
+    TASK_DTYPE = np.dtype([("sn", "<i4"), ("kind", "<i4"), ("blk", "<i4"), ("r0", "<i4"), ("nr", "<i4"),
+                           ("ntile", "<i4"), ("nbelow", "<i4"), ("xq0", "<i4"), ("tile0", "<i8")])
+
+    def big_plan(self):
+        """Dense-solve plan of the big supernodes (host data, available on analyze_only handles)."""
+        lib = _lib.load()
+        cnt = np.zeros(6, np.int64)
+        lib.tlpb200_debug_big_plan(self._h, cnt.ctypes.data_as(C.POINTER(C.c_int64)), None, None, None)
+        pack = np.zeros(int(cnt[0]), self.PACK_DTYPE)
+        fwd = np.zeros(int(cnt[1]), self.TASK_DTYPE)
+        bwd = np.zeros(int(cnt[2]), self.TASK_DTYPE)
+        lib.tlpb200_debug_big_plan(self._h, cnt.ctypes.data_as(C.POINTER(C.c_int64)), C.c_void_p(pack.ctypes.data),
+                                   C.c_void_p(fwd.ctypes.data), C.c_void_p(bwd.ctypes.data))
+        return {"pack": pack, "fwd": fwd, "bwd": bwd, "n_ftiles": int(cnt[3]), "n_btiles": int(cnt[4]),
+                "xq_slots": int(cnt[5])}
 
 
 # ---- the generic functions of src/KKT/KKT.jl ---------------------------------------------------
