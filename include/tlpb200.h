@@ -129,6 +129,9 @@ int tlpb200_debug_get_lx(tlpb200_solver* s, double* lx, int64_t* xptr /* nsuper+
    #forward tasks, #backward tasks, #forward tiles, #backward tiles, #exchange slots; the arrays receive the raw
    32-byte pack records {i32 sn, r0, nr, j; i64 fdst, bdst} and 40-byte task records
    {i32 sn, kind, blk, r0, nr, ntile, nbelow, xq0; i64 tile0}.  Any pointer may be NULL. */
+/* globaltimer (ns) of every block publish of the last dense sweeps: out[0..nblk) forward, out[nblk..2 nblk) backward;
+   recorded only when TLPB200_CHAIN_TIMES was set in the environment at tlpb200_create */
+int tlpb200_debug_chain_times(tlpb200_solver* s, uint64_t* out, int64_t* nblk);
 int tlpb200_debug_big_plan(const tlpb200_solver* s, int64_t* counts, void* pack, void* fwd, void* bwd);
 
 /* ---- multi-GPU, one process per GPU (no counterpart in the reference, NEWS.md:31) -------------

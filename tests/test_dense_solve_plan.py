@@ -45,9 +45,13 @@ def _emulate(cpu, plan, rhs_perm):
         T = np.zeros((B, B))
         T[:nr, :nbj] = panel[s][r0:r0 + nr, j * B:j * B + nbj]
         That = T @ dinv[(s, j)]
-        assert np.isnan(Ft[p["fdst"]][0]) and np.isnan(Bt[p["bdst"]][0]), "tile written twice"
+        assert np.isnan(Ft[p["fdst"]][0]), "tile written twice"
         Ft[p["fdst"]] = That.T.ravel()      # [c*128 + r]
-        Bt[p["bdst"]] = That.ravel()        # [r*128 + c]
+        if p["bdst"] >= 0:
+            assert r0 < nc and np.isnan(Bt[p["bdst"]][0]), "tile written twice"
+            Bt[p["bdst"]] = That.ravel()    # [r*128 + c]
+        else:
+            assert r0 >= nc                 # rows below the columns: no backward tile (k_bwd_below)
     assert not np.isnan(Ft).any() and not np.isnan(Bt).any(), "tile never written"
     tile = lambda buf, i: buf[i].reshape(B, B).T   # M[r, c] = flat[c*128 + r]  (the kernels' load_tile pattern)
 
@@ -94,25 +98,21 @@ def _emulate(cpu, plan, rhs_perm):
             wk[f:l] = sla.solve_triangular(np.tril(P[:nc, :nc]), t_, lower=True, trans="T")
             continue
         ncb = (nc + B - 1) // B
-        nrow = len(r)
         for t in btasks[s]:
             k, nr = int(t["blk"]), int(t["nr"])
             w = np.zeros(B)
             w[:nr] = wk[f + k * B:f + k * B + nr]
             y = dinv[(s, k)] @ w
             y[:nr] *= sign[f + k * B:f + k * B + nr]
+            # k_bwd_below: rows below the columns on the unscaled panel (every big supernode with such rows is split)
+            y[:nr] -= P[nc:, k * B:k * B + nr].T @ wk[r[nc:]]
             z = dinv[(s, k)].T @ y
             acc = np.zeros(B)
-            assert t["ntile"] == t["nbelow"] + (ncb - 1 - k)
+            assert t["ntile"] == ncb - 1 - k and t["nbelow"] == 0
             for j in range(t["ntile"]):
-                if j < t["nbelow"]:
-                    idx = np.arange(nc + j * B, min(nc + (j + 1) * B, nrow))
-                    x = np.zeros(B)
-                    x[:len(idx)] = wk[r[idx]]
-                else:
-                    cb = ncb - 1 - (j - t["nbelow"])
-                    x = xq[t["xq0"] + cb * B: t["xq0"] + (cb + 1) * B]
-                    assert not np.isnan(x).any(), "backward task reads a block that was not published yet"
+                cb = ncb - 1 - j
+                x = xq[t["xq0"] + cb * B: t["xq0"] + (cb + 1) * B]
+                assert not np.isnan(x).any(), "backward task reads a block that was not published yet"
                 acc -= tile(Bt, t["tile0"] + j) @ x
             xk = z + acc
             xq[t["xq0"] + k * B: t["xq0"] + (k + 1) * B] = xk

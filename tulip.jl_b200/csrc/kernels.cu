@@ -421,8 +421,15 @@ __global__ void __launch_bounds__(SL_THREADS, 1) k_bwd_large(DevCtx c, int32_t b
         for (int cc = 0; cc < 32; ++cc) p[cc] = 0.0;
         const double* colbase = panel + (int64_t)(i * SBLK + cg * 32) * ld;
         const int32_t ncv = min(32, max(0, I.nr - cg * 32));     // valid columns of this group
-        // rows below the supernode's columns: their x is final (ancestors were solved earlier)
-        for (int32_t r0 = nc; r0 < nrow; r0 += SBLK) {
+        // rows below the supernode's columns: their x is final (ancestors were solved earlier).  Tall supernodes had
+        // this part accumulated into bacc by k_bwd_below (consumed and re-zeroed here).
+        const bool split = c.sn_split[s] != 0;
+        double pown = 0.0;
+        if (split && tid < SBLK && tid < I.nr) {
+            pown = __ldcg(c.bacc + f + i * SBLK + tid);
+            c.bacc[f + i * SBLK + tid] = 0.0;
+        }
+        for (int32_t r0 = split ? nrow : nc; r0 < nrow; r0 += SBLK) {
             const int32_t rr = r0 + r;
             if (rr < nrow) {
                 const double xr = __ldcg(c.wk + c.sn_rows[rp + rr]);
@@ -457,7 +464,7 @@ __global__ void __launch_bounds__(SL_THREADS, 1) k_bwd_large(DevCtx c, int32_t b
         red[wq * SBLK + cg * 32 + lane] = p[0];          // 4 warps (row quarters) per column group
         __syncthreads();
         double part = 0.0;                               // thread tid < 128 owns column tid of block i
-        if (tid < SBLK) part = red[tid] + red[SBLK + tid] + red[2 * SBLK + tid] + red[3 * SBLK + tid];
+        if (tid < SBLK) part = pown + red[tid] + red[SBLK + tid] + red[2 * SBLK + tid] + red[3 * SBLK + tid];
         // the adjacent block (i+1) is the one on the critical chain: its tile was stored transposed at
         // factorisation time, so it can be prefetched into registers before the wait and applied row-wise
         if (i + 1 < ncb) {
@@ -493,6 +500,58 @@ __global__ void __launch_bounds__(SL_THREADS, 1) k_bwd_large(DevCtx c, int32_t b
         __syncthreads();
         if (tid == 0) st_release(bflag + db + i, 1);
     }
+}
+
+// backward sweep, rows below the columns of a tall supernode: bacc[column] += sum_rows L[row, column] x[row] for one
+// (column block, row range) item.  Runs as its own launch before the level's block solves: every x[row] is final
+// (ancestors), so the items are independent and fill the machine instead of one CTA walking all the rows.
+__global__ void __launch_bounds__(SL_THREADS, 1) k_bwd_below(DevCtx c, int32_t begin) {
+    __shared__ double red[SL_CG * SBLK];
+    const BelowItem I = c.bwd_below[begin + blockIdx.x];
+    const int32_t s = I.sn;
+    if (c.skip && c.skip[s]) return;
+    const int tid = threadIdx.x, r = tid & (SBLK - 1), cg = tid >> 7, lane = tid & 31, wq = (tid >> 5) & 3;
+    const int32_t f = c.sn_first[s];
+    const int32_t nc = c.sn_first[s + 1] - f;
+    const int64_t rp = c.sn_rowptr[s];
+    const int32_t ld = (int32_t)(c.sn_rowptr[s + 1] - rp);
+    const int32_t i = I.blk;
+    const int32_t nbi = min(SBLK, nc - i * SBLK);
+    const double* colbase = c.Lx + c.sn_xptr[s] + (int64_t)(i * SBLK + cg * 32) * ld;
+    const int32_t ncv = min(32, max(0, nbi - cg * 32));
+    double p[32];
+#pragma unroll
+    for (int cc = 0; cc < 32; ++cc) p[cc] = 0.0;
+    const int32_t rend = I.r0 + I.nr;
+#pragma unroll 1
+    for (int32_t r0 = I.r0; r0 < rend; r0 += SBLK) {
+        const int32_t rr = r0 + r;
+        if (rr < rend) {
+            const double xr = __ldcg(c.wk + c.sn_rows[rp + rr]);
+#pragma unroll
+            for (int c0 = 0; c0 < 32; c0 += 8) {   // 8 loads in flight per thread (keeps the kernel out of local memory)
+                double v[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] = (c0 + q < ncv) ? __ldcs(colbase + (int64_t)(c0 + q) * ld + rr) : 0.0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) p[c0 + q] += v[q] * xr;
+                asm volatile("" ::: "memory");
+            }
+        }
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int k = 0; k < off; ++k) {
+            const double send = up ? p[k] : p[k + off];
+            const double keep = up ? p[k + off] : p[k];
+            p[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    red[wq * SBLK + cg * 32 + lane] = p[0];
+    __syncthreads();
+    if (tid < nbi) atomicAdd(c.bacc + f + i * SBLK + tid, red[tid] + red[SBLK + tid] + red[2 * SBLK + tid] + red[3 * SBLK + tid]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -598,6 +657,9 @@ void launch_fwd_large(const DevCtx& c, int32_t begin, int32_t end, int nsm, cuda
 }
 void launch_bwd_large(const DevCtx& c, int32_t begin, int32_t end, int nsm, cudaStream_t st) {
     if (end > begin) k_bwd_large<<<min(end - begin, nsm), SL_THREADS, SL_SMEM, st>>>(c, begin, end);
+}
+void launch_bwd_below(const DevCtx& c, int32_t begin, int32_t end, cudaStream_t st) {
+    if (end > begin) k_bwd_below<<<(unsigned)(end - begin), SL_THREADS, 0, st>>>(c, begin);
 }
 void launch_zero_unowned(const DevCtx& c, const int8_t* keep, cudaStream_t st) {
     if (c.N > 0) k_zero_unowned<<<nblk(c.N, 256), 256, 0, st>>>(c, keep);

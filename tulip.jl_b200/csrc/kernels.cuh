@@ -53,6 +53,11 @@ struct DevCtx {
     double* Bt;                    // backward tiles (row-major 128x128, contiguous)
     unsigned long long* xq;        // exchange slots: {bits(x), bits(x) ^ key(epoch)} per entry
     unsigned long long* epoch;     // [0] sweep counter (bumped by the last CTA of every dense sweep), [1] exit counter
+    unsigned long long* dbg_ts;    // [2 * nxblk] globaltimer at every block publish (forward, then backward); nullptr = off
+    int32_t nxblk;                 // xq_slots / 128
+    const BelowItem* bwd_below;
+    const int32_t* sn_split;       // [nsuper] 1 = rows below the columns are accumulated into bacc by k_bwd_below
+    double* bacc;                  // [N] backward accumulator sum_rows L[row, c] x[row]; consumers re-zero their entries
     const int8_t* skip;   // multi-GPU: skip[s] != 0 -> supernode s is not processed in this phase on this rank (nullptr: none)
 };
 
@@ -110,6 +115,7 @@ void launch_fwd_small(const DevCtx& c, int32_t begin, int32_t end, cudaStream_t 
 void launch_bwd_small(const DevCtx& c, int32_t begin, int32_t end, cudaStream_t st);
 void launch_fwd_large(const DevCtx& c, int32_t begin, int32_t end, int nsm, cudaStream_t st);
 void launch_bwd_large(const DevCtx& c, int32_t begin, int32_t end, int nsm, cudaStream_t st);
+void launch_bwd_below(const DevCtx& c, int32_t begin, int32_t end, cudaStream_t st);
 
 void launch_pack_big(const DevCtx& c, int32_t begin, int32_t end, cudaStream_t st);
 void launch_fwd_big(const DevCtx& c, int32_t begin, int32_t end, int nsm, cudaStream_t st);

@@ -46,6 +46,12 @@ __device__ __forceinline__ double poll_slot(const unsigned long long* slot, unsi
     return __longlong_as_double((long long)a);
 }
 
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+    return t;
+}
+
 __device__ __forceinline__ void prefetch_l2(const void* p, unsigned bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(p), "r"(bytes) : "memory");
 }
@@ -137,6 +143,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) k_pack_big(DevCtx c, int32_t be
             *reinterpret_cast<double2*>(d) = make_double2(o[0][b], o[1][b]);
             *reinterpret_cast<double2*>(d + 2) = make_double2(o[2][b], o[3][b]);
         }
+        if (P.bdst >= 0)
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
             double* d = bout + (row0 + a) * SBLK + tj * 8;
@@ -206,6 +213,7 @@ __global__ void __launch_bounds__(BG_THREADS, 1) k_fwd_big(DevCtx c, int32_t beg
                 const double w = bown + v;   // rows beyond nr: zero tiles, bown = 0 -> publishes 0
                 publish_slot(xq + 2 * (T.blk * SBLK + tid), w, key);
                 if (tid < T.nr) c.wk[f + T.r0 + tid] = w;
+                if (c.dbg_ts && tid == 0) c.dbg_ts[T.xq0 / SBLK + T.blk] = global_ns();
             } else if (tid < T.nr) {
                 atomicAdd(c.wk + c.sn_rows[rp + T.r0 + tid], v);
             }
@@ -215,7 +223,8 @@ __global__ void __launch_bounds__(BG_THREADS, 1) k_fwd_big(DevCtx c, int32_t beg
     leave_sweep(c.epoch);
 }
 
-// backward:  z_k = L_kk^{-T} S L_kk^{-1} w_k ;  x_k = z_k - sum_{rows below} Lhat[row, k]' x_row
+// backward:  z_k = L_kk^{-T} (S L_kk^{-1} w_k - p_k) ;  x_k = z_k - sum_{j>k} Lhat_jk' x_j
+// (p_k = contribution of the rows below the supernode's columns, accumulated by k_bwd_below on the unscaled panel)
 __global__ void __launch_bounds__(BG_THREADS, 1) k_bwd_big(DevCtx c, int32_t begin, int32_t end) {
     __shared__ BgShared sh;
     const int tid = threadIdx.x, r = tid & (SBLK - 1), cg = tid >> 7;
@@ -226,8 +235,6 @@ __global__ void __launch_bounds__(BG_THREADS, 1) k_bwd_big(DevCtx c, int32_t beg
         if (c.skip && c.skip[s]) continue;
         const int32_t f = c.sn_first[s];
         const int32_t nc = c.sn_first[s + 1] - f;
-        const int64_t rp = c.sn_rowptr[s];
-        const int32_t nrow = (int32_t)(c.sn_rowptr[s + 1] - rp);
         const int32_t ncb = (nc + SBLK - 1) / SBLK;
         const int32_t k = T.blk;
         const double* tiles = c.Bt + T.tile0 * TILE_ELEMS;
@@ -242,10 +249,15 @@ __global__ void __launch_bounds__(BG_THREADS, 1) k_bwd_big(DevCtx c, int32_t beg
         sh.red[cg][r] = dot_tile(t, sh.xs[0], cg);
         load_tile(t, c.DinvT + db, r, cg);
         __syncthreads();
-        if (tid < SBLK)
-            sh.xs[1][tid] = (tid < T.nr) ? (double)c.sign[f + k * SBLK + tid] *
-                                               (sh.red[0][tid] + sh.red[1][tid] + sh.red[2][tid] + sh.red[3][tid])
-                                         : 0.0;
+        if (tid < SBLK) {   // y = S L_kk^{-1} w_k - (rows below the columns, accumulated by k_bwd_below; re-zeroed here)
+            double y = 0.0;
+            if (tid < T.nr) {
+                y = (double)c.sign[f + k * SBLK + tid] * (sh.red[0][tid] + sh.red[1][tid] + sh.red[2][tid] + sh.red[3][tid]) -
+                    __ldcg(c.bacc + f + k * SBLK + tid);
+                c.bacc[f + k * SBLK + tid] = 0.0;
+            }
+            sh.xs[1][tid] = y;
+        }
         __syncthreads();
         sh.red[cg][r] = dot_tile(t, sh.xs[1], cg);
         if (T.ntile > 0) load_tile(t, tiles, r, cg);
@@ -258,15 +270,7 @@ __global__ void __launch_bounds__(BG_THREADS, 1) k_bwd_big(DevCtx c, int32_t beg
             if (tid < 4 && j + 2 < T.ntile)
                 prefetch_l2(tiles + (int64_t)(j + 2) * TILE_ELEMS + tid * (TILE_ELEMS / 4), TILE_ELEMS * 2);
             double* xs = sh.xs[j & 1];
-            if (tid < SBLK) {
-                if (j < T.nbelow) {   // rows below the supernode's columns: x is final (ancestors)
-                    const int32_t idx = nc + j * SBLK + tid;
-                    xs[tid] = (idx < nrow) ? __ldcg(c.wk + c.sn_rows[rp + idx]) : 0.0;
-                } else {
-                    const int32_t cb = ncb - 1 - (j - T.nbelow);
-                    xs[tid] = poll_slot(xq + 2 * (cb * SBLK + tid), key, c.info);
-                }
-            }
+            if (tid < SBLK) xs[tid] = poll_slot(xq + 2 * ((ncb - 1 - j) * SBLK + tid), key, c.info);
             __syncthreads();
             acc -= dot_tile(t, xs, cg);
             if (j + 1 < T.ntile) load_tile(t, tiles + (int64_t)(j + 1) * TILE_ELEMS, r, cg);
@@ -277,6 +281,7 @@ __global__ void __launch_bounds__(BG_THREADS, 1) k_bwd_big(DevCtx c, int32_t beg
             const double x = zown + sh.red[0][tid] + sh.red[1][tid] + sh.red[2][tid] + sh.red[3][tid];
             publish_slot(xq + 2 * (k * SBLK + tid), x, key);
             if (tid < T.nr) c.wk[f + k * SBLK + tid] = x;
+            if (c.dbg_ts && tid == 0) c.dbg_ts[c.nxblk + T.xq0 / SBLK + k] = global_ns();
         }
         __syncthreads();
     }

@@ -55,6 +55,8 @@ void build_plan(const Symbolic& S, const PlanOptions& opt, Plan& P) {
     P.sn_level.assign(ns, 0);
     P.sn_dblk.assign(ns, -1);
     P.sn_big.assign(ns, 0);
+    P.sn_split.assign(ns, 0);
+    P.bwd_below.clear();
     P.big_pack.clear();
     P.fwd_big.clear();
     P.bwd_big.clear();
@@ -270,7 +272,7 @@ void build_plan(const Symbolic& S, const PlanOptions& opt, Plan& P) {
                 ftile0[x].resize(ncb + nbb);
                 btile0[x].resize(ncb);
                 for (int32_t b = 0; b < ncb + nbb; ++b) { ftile0[x][b] = P.n_ftiles; P.n_ftiles += (b < ncb) ? b : ncb; }
-                for (int32_t k = 0; k < ncb; ++k) { btile0[x][k] = P.n_btiles; P.n_btiles += nbb + (ncb - 1 - k); }
+                for (int32_t k = 0; k < ncb; ++k) { btile0[x][k] = P.n_btiles; P.n_btiles += ncb - 1 - k; }
                 // one pack task per tile: block row b (column block or below block) x column block j
                 for (int32_t b = 0; b < ncb + nbb; ++b) {
                     const int32_t rr0 = (b < ncb) ? b * SBLK : nc + (b - ncb) * SBLK;   // below blocks start at row nc
@@ -283,7 +285,7 @@ void build_plan(const Symbolic& S, const PlanOptions& opt, Plan& P) {
                         pk.nr = rnr;
                         pk.j = j;
                         pk.fdst = ftile0[x][b] + j;
-                        pk.bdst = btile0[x][j] + ((b < ncb) ? nbb + (ncb - 1 - b) : (b - ncb));
+                        pk.bdst = (b < ncb) ? btile0[x][j] + (ncb - 1 - b) : -1;
                         P.big_pack.push_back(pk);
                     }
                 }
@@ -306,8 +308,8 @@ void build_plan(const Symbolic& S, const PlanOptions& opt, Plan& P) {
             for (int32_t d = 0; d < maxcb; ++d)
                 for (size_t x = 0; x < nb_; ++x) {
                     const int32_t s = lbig[L][x];
-                    const int32_t nc = sn_ncol(S, s), nr = sn_nrow(S, s);
-                    const int32_t ncb = (nc + SBLK - 1) / SBLK, nbb = (nr - nc + SBLK - 1) / SBLK;
+                    const int32_t nc = sn_ncol(S, s);
+                    const int32_t ncb = (nc + SBLK - 1) / SBLK;
                     if (d >= ncb) continue;
                     BigTask t;
                     t.sn = s;
@@ -315,8 +317,8 @@ void build_plan(const Symbolic& S, const PlanOptions& opt, Plan& P) {
                     t.blk = ncb - 1 - d;
                     t.r0 = t.blk * SBLK;
                     t.nr = std::min(SBLK, nc - t.r0);
-                    t.nbelow = nbb;
-                    t.ntile = nbb + d;
+                    t.nbelow = 0;
+                    t.ntile = d;
                     t.xq0 = xq0[x];
                     t.tile0 = btile0[x][t.blk];
                     P.bwd_big.push_back(t);
@@ -324,6 +326,26 @@ void build_plan(const Symbolic& S, const PlanOptions& opt, Plan& P) {
         }
         lp.fbig_end = (int32_t)P.fwd_big.size();
         lp.bbig_end = (int32_t)P.bwd_big.size();
+
+        // backward "below" items of the tall supernodes that start at this level
+        lp.below_begin = (int32_t)P.bwd_below.size();
+        for (int pass = 0; pass < 2; ++pass)
+            for (int32_t s : (pass == 0 ? lbig[L] : llarge[L])) {
+                const int32_t nc = sn_ncol(S, s), nr = sn_nrow(S, s);
+                if (nr == nc || (pass == 1 && nr - nc < SPLIT_ROWS)) continue;
+                P.sn_split[s] = 1;
+                const int32_t ncb = (nc + SBLK - 1) / SBLK;
+                for (int32_t k = 0; k < ncb; ++k)
+                    for (int32_t r0 = nc; r0 < nr; r0 += BELOW_ROWS) {
+                        BelowItem bi;
+                        bi.sn = s;
+                        bi.blk = k;
+                        bi.r0 = r0;
+                        bi.nr = std::min(BELOW_ROWS, nr - r0);
+                        P.bwd_below.push_back(bi);
+                    }
+            }
+        lp.below_end = (int32_t)P.bwd_below.size();
     }
 }
 

@@ -14,6 +14,8 @@ constexpr int TILE = 64;      // update tile edge (urgent tiles, main stream)
 constexpr int TILE128 = 128;  // update tile edge of the persistent side-stream kernel
 constexpr int PIECE = 128;    // column-piece width of wide supernodes = solve block size
 constexpr int SBLK = 128;     // block size of the dense triangular-solve kernels (== PIECE)
+constexpr int BELOW_ROWS = 512;   // rows per backward "below" item
+constexpr int SPLIT_ROWS = 384;   // non-big supernodes with at least this many rows below their columns are split
 
 struct PlanOptions {
     int small_elems = 4096;   // supernodes with nrow*ncol <= small_elems, ncol <= small_ncol and
@@ -56,14 +58,15 @@ struct SolveItem {
 // After the factorisation the panel of a big supernode is repacked into 128x128 tiles of
 // Lhat = L * blockdiag(L_kk)^{-1} (unit block diagonal), each tile contiguous (16384 doubles, zero padded):
 //   Ft: tile (I, j) column-major   [c*128 + r] = Lhat[I.r0 + r, j*128 + c]   (forward sweep, block row I)
-//   Bt: the same tile row-major    [r*128 + c]                               (backward sweep, block column j)
+//   Bt: the same tile row-major    [r*128 + c]                               (backward sweep, block column j;
+//       only the tiles inside the supernode's columns: the rows below are BelowItems on the unscaled panel)
 // The tiles of one solve task are contiguous in the order the task streams them.
 struct BigPack {
     int32_t sn;
     int32_t r0, nr;   // row range of the tile inside the supernode's row list
     int32_t j;        // column block
     int64_t fdst;     // tile index inside Ft
-    int64_t bdst;     // tile index inside Bt
+    int64_t bdst;     // tile index inside Bt (-1: none)
 };
 
 struct BigTask {
@@ -71,10 +74,17 @@ struct BigTask {
     int32_t kind;     // forward: 0 = block row inside the columns, 1 = block of rows below.  backward: 0
     int32_t blk;      // column block (kind 0) / below block (kind 1)
     int32_t r0, nr;   // row range inside the supernode's row list
-    int32_t ntile;    // tiles streamed: forward kind 0: blk, kind 1: ncb; backward: nbelow + (ncb-1-blk)
-    int32_t nbelow;   // backward: leading tiles whose x is gathered from wk through the row list
+    int32_t ntile;    // tiles streamed: forward kind 0: blk, kind 1: ncb; backward: ncb-1-blk
+    int32_t nbelow;   // unused (the rows below the columns are BelowItems in the backward sweep)
     int32_t xq0;      // first exchange slot of the supernode (slot = xq0 + column offset inside the supernode)
     int64_t tile0;    // first tile inside Ft / Bt
+};
+
+// backward sweep, rows below the columns of a tall supernode: p = L[rows, block]' x[rows] is accumulated into
+// DevCtx::bacc by a separate, fully parallel launch (k_bwd_below) before the level's block solves run
+struct BelowItem {
+    int32_t sn, blk;   // supernode, column block
+    int32_t r0, nr;    // row range inside the supernode's row list (r0 >= ncol)
 };
 
 struct LevelPlan {
@@ -89,6 +99,7 @@ struct LevelPlan {
     int32_t bwd_begin = 0, bwd_end = 0;        // Plan::bwd_items
     int32_t fbig_begin = 0, fbig_end = 0;      // Plan::fwd_big (big supernodes that start at this level)
     int32_t bbig_begin = 0, bbig_end = 0;      // Plan::bwd_big
+    int32_t below_begin = 0, below_end = 0;    // Plan::bwd_below
 };
 
 struct Plan {
@@ -112,6 +123,8 @@ struct Plan {
     std::vector<int32_t> sn_big;          // [nsuper] 1 = dense-solve path
     std::vector<BigPack> big_pack;
     std::vector<BigTask> fwd_big, bwd_big;
+    std::vector<int32_t> sn_split;        // [nsuper] 1 = the rows below the columns are handled by BelowItems in the backward sweep
+    std::vector<BelowItem> bwd_below;
     int64_t n_ftiles = 0, n_btiles = 0;   // tiles of Ft / Bt
     int32_t xq_slots = 0;                 // exchange slots (sum over big supernodes of ncb*128)
     std::vector<LevelPlan> levels;

@@ -283,6 +283,7 @@ void enqueue_bwd(tlpb200_solver* s, int64_t& count) {
     const auto& L = s->plan.levels;
     for (size_t l = L.size(); l-- > 0;) {
         const LevelPlan& lp = L[l];
+        if (lp.below_end > lp.below_begin) { Scope sc(s, 9); launch_bwd_below((*s->cur), lp.below_begin, lp.below_end, st); count++; }
         if (lp.bbig_end > lp.bbig_begin) { Scope sc(s, 15); launch_bwd_big((*s->cur), lp.bbig_begin, lp.bbig_end, s->nsm, st); count++; }
         if (lp.bwd_end > lp.bwd_begin) { Scope sc(s, 9); launch_bwd_large((*s->cur), lp.bwd_begin, lp.bwd_end, s->nsm, st); count++; }
         if (lp.small_end > lp.small_begin) { Scope sc(s, 11); launch_bwd_small((*s->cur), lp.small_begin, lp.small_end, st); count++; }
@@ -514,8 +515,18 @@ void setup_device(tlpb200_solver* s) {
     c.bwd_big = upload(s, P.bwd_big);
     c.Ft = dalloc<double>(s, (size_t)P.n_ftiles * SBLK * SBLK);
     c.Bt = dalloc<double>(s, (size_t)P.n_btiles * SBLK * SBLK);
+    c.bwd_below = upload(s, P.bwd_below);
+    c.sn_split = upload(s, P.sn_split);
+    c.bacc = dalloc<double>(s, (size_t)S.N);
+    CK(cudaMemset(c.bacc, 0, std::max<size_t>(S.N, 1) * sizeof(double)));
     c.xq = dalloc<unsigned long long>(s, (size_t)2 * P.xq_slots);
     CK(cudaMemset(c.xq, 0, std::max<size_t>(2 * (size_t)P.xq_slots, 1) * sizeof(unsigned long long)));
+    c.nxblk = P.xq_slots / SBLK;
+    c.dbg_ts = nullptr;
+    if (getenv("TLPB200_CHAIN_TIMES")) {
+        c.dbg_ts = dalloc<unsigned long long>(s, (size_t)2 * c.nxblk);
+        CK(cudaMemset(c.dbg_ts, 0, std::max<size_t>(2 * (size_t)c.nxblk, 1) * sizeof(unsigned long long)));
+    }
     c.epoch = dalloc<unsigned long long>(s, 2);
     CK(cudaMemset(c.epoch, 0, 2 * sizeof(unsigned long long)));
     c.wk = dalloc<double>(s, (size_t)S.N);
@@ -911,6 +922,17 @@ int tlpb200_debug_get_lx(tlpb200_solver* s, double* lx, int64_t* xptr) {
     } catch (const CudaFail& f) {
         return cuda_fail(s, f);
     }
+}
+
+/* globaltimer (ns) of every block publish of the last dense sweeps: out[0..nblk) forward, out[nblk..2 nblk) backward;
+   only recorded when the solver was created with TLPB200_CHAIN_TIMES set in the environment */
+int tlpb200_debug_chain_times(tlpb200_solver* s, uint64_t* out, int64_t* nblk) {
+    REQUIRE_DEVICE(s);
+    if (nblk) *nblk = s->ctx.nxblk;
+    if (!s->ctx.dbg_ts) return fail(s, TLPB200_BAD_ARG, "chain times were not recorded (TLPB200_CHAIN_TIMES unset at setup)");
+    cudaStreamSynchronize(s->stream);
+    if (out) cudaMemcpy(out, s->ctx.dbg_ts, (size_t)2 * s->ctx.nxblk * sizeof(uint64_t), cudaMemcpyDeviceToHost);
+    return TLPB200_OK;
 }
 
 int tlpb200_debug_big_plan(const tlpb200_solver* s, int64_t* counts, void* pack, void* fwd, void* bwd) {

@@ -275,6 +275,18 @@ class B200KKTSolver:
     TASK_DTYPE = np.dtype([("sn", "<i4"), ("kind", "<i4"), ("blk", "<i4"), ("r0", "<i4"), ("nr", "<i4"),
                            ("ntile", "<i4"), ("nbelow", "<i4"), ("xq0", "<i4"), ("tile0", "<i8")])
 
+    def chain_times(self):
+        """(forward, backward) globaltimer stamps [ns] of every block publish of the last dense sweeps
+        (needs TLPB200_CHAIN_TIMES=1 in the environment at setup)."""
+        lib = _lib.load()
+        nb = C.c_int64(0)
+        lib.tlpb200_debug_chain_times(self._h, None, C.byref(nb))
+        out = np.zeros(2 * nb.value, np.uint64)
+        rc = lib.tlpb200_debug_chain_times(self._h, C.c_void_p(out.ctypes.data), C.byref(nb))
+        if rc != _lib.OK:
+            _raise(rc, self._h)
+        return out[:nb.value].astype(np.int64), out[nb.value:].astype(np.int64)
+
     def big_plan(self):
         """Dense-solve plan of the big supernodes (host data, available on analyze_only handles)."""
         lib = _lib.load()
