@@ -159,11 +159,11 @@ def test_dense_solve_path_parity(name, gen, sysname, ncol):
         for k in (kd, kb, o):
             dx = np.zeros(n); dy = np.zeros(m)
             k.solve(dx, dy, xi_p, xi_d)
-            if k is kd:                                   # same rhs twice on the same factor: bitwise-stable hand-over
-                dx2 = np.zeros(n); dy2 = np.zeros(m)
+            if k is kd:                                   # same rhs again on the same factor: the exchange slots are reused
+                dx2 = np.zeros(n); dy2 = np.zeros(m)        # (equal up to the rounding of the atomic accumulations)
                 k.solve(dx2, dy2, xi_p, xi_d)
-                assert np.allclose(dx2, dx, rtol=1e-12, atol=1e-12 * np.abs(dx).max())
-                assert np.allclose(dy2, dy, rtol=1e-12, atol=1e-12 * np.abs(dy).max())
+                assert np.abs(dx2 - dx).max() <= 1e-9 * np.abs(dx).max(), np.abs(dx2 - dx).max() / np.abs(dx).max()
+                assert np.abs(dy2 - dy).max() <= 1e-9 * np.abs(dy).max(), np.abs(dy2 - dy).max() / np.abs(dy).max()
             sols.append(np.concatenate([dx, dy]))
         ref = np.abs(sols[2]).max()
         assert np.abs(sols[0] - sols[2]).max() / ref < 1e-8, np.abs(sols[0] - sols[2]).max() / ref

@@ -174,11 +174,11 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_small_factor(DevCtx c, int32_
 // ------------------------------------------------------------------------------------------
 constexpr int INV_THREADS = SBLK;
 
-__global__ void __launch_bounds__(INV_THREADS) k_invert_diag(DevCtx c) {
+__global__ void __launch_bounds__(INV_THREADS) k_invert_diag(DevCtx c, int32_t begin) {
     extern __shared__ double smem_d[];
     double* Cs = smem_d;                 // [SBLK][SBLK+1] column-major: L on entry, X = L^{-1} on exit
     const int LDI = SBLK + 1;
-    const int32_t b = blockIdx.x;
+    const int32_t b = c.inv_order[begin + blockIdx.x];
     const int32_t s = c.dblk_sn[b], bi = c.dblk_idx[b];
     if (c.skip && c.skip[s]) return;
     const int32_t f = c.sn_first[s];
@@ -643,8 +643,8 @@ cudaError_t kernels_static_init() {
 void launch_small_factor(const DevCtx& c, int32_t begin, int32_t end, size_t smem, cudaStream_t st) {
     if (end > begin) k_small_factor<<<end - begin, SMALL_THREADS, smem, st>>>(c, begin);
 }
-void launch_invert_diag(const DevCtx& c, cudaStream_t st) {
-    if (c.ndblk > 0) k_invert_diag<<<c.ndblk, INV_THREADS, INV_SMEM, st>>>(c);
+void launch_invert_diag(const DevCtx& c, int32_t begin, int32_t end, cudaStream_t st) {
+    if (end > begin) k_invert_diag<<<end - begin, INV_THREADS, INV_SMEM, st>>>(c, begin);
 }
 void launch_fwd_small(const DevCtx& c, int32_t begin, int32_t end, cudaStream_t st) {
     if (end > begin) k_fwd_small<<<nblk(end - begin, SOLVE_SMALL_WARPS), 32 * SOLVE_SMALL_WARPS, 0, st>>>(c, begin, end);

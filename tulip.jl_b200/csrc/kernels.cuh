@@ -34,6 +34,7 @@ struct DevCtx {
     const int32_t* sn_dblk;    // [nsuper] first diagonal block of a non-small supernode
     const int32_t* dblk_sn;    // [ndblk]
     const int32_t* dblk_idx;   // [ndblk]
+    const int32_t* inv_order;  // [ndblk] diagonal blocks sorted by level
     // numeric state
     double* Lx;
     double* Dinv;    // [ndblk][128*128] explicit inverses of the diagonal blocks (column-major, lower)
@@ -109,7 +110,7 @@ void launch_diag_factor(const DevCtx& c, int32_t begin, int32_t end, cudaStream_
 void launch_trsm(const DevCtx& c, int32_t begin, int32_t end, cudaStream_t st);
 void launch_update(const DevCtx& c, int32_t begin, int32_t end, int atomic, cudaStream_t st);
 void launch_update_lazy(const DevCtx& c, int32_t begin, int32_t end, int32_t* counter, int nsm, int reserve, cudaStream_t st);
-void launch_invert_diag(const DevCtx& c, cudaStream_t st);
+void launch_invert_diag(const DevCtx& c, int32_t begin, int32_t end, cudaStream_t st);   // range of DevCtx::inv_order
 
 void launch_fwd_small(const DevCtx& c, int32_t begin, int32_t end, cudaStream_t st);
 void launch_bwd_small(const DevCtx& c, int32_t begin, int32_t end, cudaStream_t st);

@@ -210,6 +210,56 @@ void build_plan(const Symbolic& S, const PlanOptions& opt, Plan& P) {
         lp.lazy_end = (int32_t)P.upd128.size();
         lp.ext_atomic = 1;
 
+        // Critical subset: the update tiles that land in a diagonal block of a next-level piece or anywhere in a
+        // next-level small supernode are all that the first kernels of level L+1 (one-CTA supernodes, diagonal
+        // blocks) wait for; the row tiles of the trsm they read are the critical part of the trsm.  Both lists
+        // are reordered critical-first so that the chain can run them ahead of the rest (solver.cu).
+        {
+            std::vector<char> ucrit(lp.ext_end - lp.ext_begin, 0);
+            std::vector<std::vector<char>> rowmark(lpiece[L].size());
+            auto piece_slot = [&](int32_t p) { return (size_t)(std::lower_bound(lpiece[L].begin(), lpiece[L].end(), p) - lpiece[L].begin()); };
+            for (int32_t x = lp.ext_begin; x < lp.ext_end; ++x) {
+                const UpdTask& T = P.upd[x];
+                const int32_t s = P.pieces[T.piece].sn;
+                const int32_t* rows = S.sn_rows.data() + S.sn_rowptr[s];
+                bool cr = false;
+                for (int32_t k = T.k0; k < T.k0 + T.nk && !cr; ++k) {
+                    const int32_t gk = rows[k];
+                    if (col_level[gk] != L + 1) continue;
+                    const int32_t ts = S.col2sn[gk];
+                    if (P.sn_small[ts]) { cr = true; break; }
+                    const int32_t pf = S.sn_first[ts] + ((gk - S.sn_first[ts]) / PIECE) * PIECE;
+                    const int32_t pl = std::min(pf + PIECE, S.sn_first[ts + 1]);
+                    for (int32_t i = T.i0; i < T.i0 + T.ni; ++i)
+                        if (rows[i] >= pf && rows[i] < pl) { cr = true; break; }
+                }
+                if (!cr) continue;
+                ucrit[x - lp.ext_begin] = 1;
+                std::vector<char>& mk = rowmark[piece_slot(T.piece)];
+                if (mk.empty()) mk.assign(sn_nrow(S, s), 0);
+                for (int32_t i = T.i0; i < T.i0 + T.ni; ++i) mk[i] = 1;
+                for (int32_t k = T.k0; k < T.k0 + T.nk; ++k) mk[k] = 1;
+            }
+            std::vector<UpdTask> a, b;
+            for (int32_t x = lp.ext_begin; x < lp.ext_end; ++x) (ucrit[x - lp.ext_begin] ? a : b).push_back(P.upd[x]);
+            std::copy(a.begin(), a.end(), P.upd.begin() + lp.ext_begin);
+            std::copy(b.begin(), b.end(), P.upd.begin() + lp.ext_begin + (int32_t)a.size());
+            lp.ext_crit_end = lp.ext_begin + (int32_t)a.size();
+            std::vector<PanelTask> pa, pb;
+            for (int32_t x = lp.panel_begin; x < lp.panel_end; ++x) {
+                const PanelTask& pt = P.panel[x];
+                const std::vector<char>& mk = rowmark[piece_slot(pt.piece)];
+                bool cr = false;
+                if (!mk.empty())
+                    for (int32_t r = pt.r0; r < pt.r0 + pt.nr; ++r)
+                        if (mk[r]) { cr = true; break; }
+                (cr ? pa : pb).push_back(pt);
+            }
+            std::copy(pa.begin(), pa.end(), P.panel.begin() + lp.panel_begin);
+            std::copy(pb.begin(), pb.end(), P.panel.begin() + lp.panel_begin + (int32_t)pa.size());
+            lp.panel_crit_end = lp.panel_begin + (int32_t)pa.size();
+        }
+
         // dense block-solve items of the supernodes that *start* at this level, in wavefront order
         // (block index major) so that every dependency of an item precedes it in the list
         lp.fwd_begin = (int32_t)P.fwd_items.size();
@@ -346,6 +396,25 @@ void build_plan(const Symbolic& S, const PlanOptions& opt, Plan& P) {
                     }
             }
         lp.below_end = (int32_t)P.bwd_below.size();
+    }
+
+    // diagonal blocks and pack tiles in level order: solver.cu starts inverting / repacking the columns that are
+    // final while the tail of the factorisation (which leaves most SMs idle) is still running
+    P.inv_order.resize(P.pieces.size());
+    for (int32_t p = 0; p < (int32_t)P.pieces.size(); ++p) P.inv_order[p] = p;
+    std::stable_sort(P.inv_order.begin(), P.inv_order.end(),
+                     [&](int32_t a, int32_t b) { return P.pieces[a].level < P.pieces[b].level; });
+    auto pack_level = [&](const BigPack& k) { return P.pieces[P.sn_dblk[k.sn] + k.j].level; };
+    std::stable_sort(P.big_pack.begin(), P.big_pack.end(),
+                     [&](const BigPack& a, const BigPack& b) { return pack_level(a) < pack_level(b); });
+    {
+        size_t ii = 0, pp = 0;
+        for (int32_t L = 0; L < nlev; ++L) {
+            while (ii < P.inv_order.size() && P.pieces[P.inv_order[ii]].level <= L) ++ii;
+            while (pp < P.big_pack.size() && pack_level(P.big_pack[pp]) <= L) ++pp;
+            P.levels[L].inv_end = (int32_t)ii;
+            P.levels[L].pack_end = (int32_t)pp;
+        }
     }
 }
 

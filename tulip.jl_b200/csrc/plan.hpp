@@ -91,7 +91,10 @@ struct LevelPlan {
     int32_t small_begin = 0, small_end = 0;    // Plan::small_list
     int32_t piece_begin = 0, piece_end = 0;    // Plan::level_pieces (diag-factor CTAs)
     int32_t panel_begin = 0, panel_end = 0;    // Plan::panel (trsm row tiles)
+    int32_t panel_crit_end = 0;                // [panel_begin, panel_crit_end): row tiles read by the critical update tiles
     int32_t ext_begin = 0, ext_end = 0;        // Plan::upd
+    int32_t ext_crit_end = 0;                  // [ext_begin, ext_crit_end): tiles that land in a diagonal block / small
+                                               // supernode of the next level (they gate its first kernels)
     int32_t urgent_end = 0;                    // == ext_end (all 64x64 tiles are urgent)
     int32_t lazy_begin = 0, lazy_end = 0;      // Plan::upd128 (128x128 tiles, side stream)
     int32_t ext_atomic = 1;
@@ -100,6 +103,8 @@ struct LevelPlan {
     int32_t fbig_begin = 0, fbig_end = 0;      // Plan::fwd_big (big supernodes that start at this level)
     int32_t bbig_begin = 0, bbig_end = 0;      // Plan::bwd_big
     int32_t below_begin = 0, below_end = 0;    // Plan::bwd_below
+    int32_t inv_end = 0;                       // Plan::inv_order[0, inv_end): diagonal blocks of pieces at levels <= this one
+    int32_t pack_end = 0;                      // Plan::big_pack[0, pack_end): tiles whose column block is at a level <= this one
 };
 
 struct Plan {
@@ -123,6 +128,7 @@ struct Plan {
     std::vector<int32_t> sn_big;          // [nsuper] 1 = dense-solve path
     std::vector<BigPack> big_pack;
     std::vector<BigTask> fwd_big, bwd_big;
+    std::vector<int32_t> inv_order;       // diagonal blocks (== piece ids) sorted by level
     std::vector<int32_t> sn_split;        // [nsuper] 1 = the rows below the columns are handled by BelowItems in the backward sweep
     std::vector<BelowItem> bwd_below;
     int64_t n_ftiles = 0, n_btiles = 0;   // tiles of Ft / Bt

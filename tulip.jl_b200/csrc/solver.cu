@@ -39,7 +39,15 @@ struct tlpb200_solver {
     bool on_device = false;
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr, side_stream = nullptr;
+    cudaStream_t side2[3] = {nullptr, nullptr, nullptr};   // further side streams: consecutive lazy batches overlap their ramp-down/up
+    int nside = 1;                                         // TLPB200_SIDE_STREAMS (1..4)
     std::vector<cudaEvent_t> ev_f, ev_lazy;   // per level: chain done / lazy update batch done
+    std::vector<cudaEvent_t> ev_d, ev_tr, ev_ur;   // per level: diagonal blocks done / rest of the trsm done / rest of the urgent tiles done
+    cudaStream_t aux_stream = nullptr;        // non-critical part of the chain kernels (TLPB200_SPLIT_CHAIN)
+    bool split_chain = true;
+    cudaEvent_t ev_pack = nullptr;
+    double pack_split = 0.55;     // TLPB200_PACK_SPLIT: level fraction at which the early invert/repack batch is issued (0 = off)
+
     std::vector<void*> allocs;
     size_t bytes_device = 0;
     DevCtx ctx{};
@@ -58,6 +66,8 @@ struct tlpb200_solver {
     int nsm = 148;
     int32_t* lazy_ctr = nullptr;   // [2*nlevels] work-queue / exit counters of the lazy update launches
     int chain_sms = 16;   // SMs kept free of the bulk-update work queue for the critical chain (TLPB200_CHAIN_SMS)
+    int chain_sms_late = -1;      // same, from level chain_switch * nlevels on (TLPB200_CHAIN_SMS_LATE; -1 = same as chain_sms)
+    double chain_switch = 0.5;    // TLPB200_CHAIN_SWITCH
 
     cudaGraphExec_t g_update = nullptr, g_solve = nullptr;
     bool profiling = false;
@@ -198,18 +208,26 @@ void enqueue_factor(tlpb200_solver* s, int64_t& count) {
             CK(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
             s->ev_f.push_back(a);
             s->ev_lazy.push_back(b);
+            cudaEvent_t c3[3];
+            for (auto& e : c3) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            s->ev_d.push_back(c3[0]);
+            s->ev_tr.push_back(c3[1]);
+            s->ev_ur.push_back(c3[2]);
         }
     }
+    // columns that are final early are inverted / repacked for the solves underneath the tail of the factorisation
+    const long pack_level = (overlap && s->pack_split > 0.0 && s->pack_split < 1.0 && !s->plan.big_pack.empty()) ? (long)(s->pack_split * (double)nlev) : -1;
+    int32_t inv_done = 0, pack_done = 0;
+    bool early_pack = false;
     std::vector<char> has_lazy(nlev, 0);
-    long last_lazy = -1;     // last level whose lazy batch was issued on the side stream
-    long waited = -1;        // last lazy level the main stream has waited for
+    long waited = -1;        // every lazy batch of a level <= waited has been joined by the main stream
+    int nbatch = 0;
     for (size_t l = 0; l < nlev; ++l) {
         const LevelPlan& lp = L[l];
-        if (overlap && l >= 2) {     // level l needs every lazy batch of levels <= l-2 (side stream is in-order)
-            long need = -1;
-            for (long q = (long)l - 2; q > waited; --q)
-                if (has_lazy[q]) { need = q; break; }
-            if (need > waited) { CK(cudaStreamWaitEvent(st, s->ev_lazy[need], 0)); waited = need; }
+        if (overlap && l >= 2) {     // level l needs every lazy batch of levels <= l-2 (RED updates commute: no order among batches)
+            for (long q = waited + 1; q <= (long)l - 2; ++q)
+                if (has_lazy[q]) CK(cudaStreamWaitEvent(st, s->ev_lazy[q], 0));
+            waited = (long)l - 2;
         }
         if (lp.small_end > lp.small_begin) {
             Scope sc(s, 1);
@@ -217,27 +235,68 @@ void enqueue_factor(tlpb200_solver* s, int64_t& count) {
             count++;
         }
         if (lp.piece_end > lp.piece_begin) { Scope sc(s, 2); launch_diag_factor((*s->cur), lp.piece_begin, lp.piece_end, st); count++; }
-        if (lp.panel_end > lp.panel_begin) { Scope sc(s, 3); launch_trsm((*s->cur), lp.panel_begin, lp.panel_end, st); count++; }
+        const bool split = overlap && s->split_chain;
+        if (!split) {
+            if (lp.panel_end > lp.panel_begin) { Scope sc(s, 3); launch_trsm((*s->cur), lp.panel_begin, lp.panel_end, st); count++; }
+        } else {
+            // Chain (main stream): diagonal blocks -> critical trsm row tiles -> critical update tiles -> next level's
+            // diagonal blocks.  The rest of the trsm and of the urgent tiles runs on the aux stream underneath the next
+            // diagonal-block factorisation; the next level's trsm joins it.
+            CK(cudaEventRecord(s->ev_d[l], st));
+            CK(cudaStreamWaitEvent(s->aux_stream, s->ev_d[l], 0));
+            if (lp.panel_end > lp.panel_crit_end) { launch_trsm((*s->cur), lp.panel_crit_end, lp.panel_end, s->aux_stream); count++; }
+            CK(cudaEventRecord(s->ev_tr[l], s->aux_stream));
+            if (l > 0) CK(cudaStreamWaitEvent(st, s->ev_ur[l - 1], 0));   // rest of the previous level's urgent tiles
+            if (lp.panel_crit_end > lp.panel_begin) { launch_trsm((*s->cur), lp.panel_begin, lp.panel_crit_end, st); count++; }
+        }
         // the persistent bulk kernel leaves `chain_sms` SMs to the critical-chain kernels
         if (lp.lazy_end > lp.lazy_begin) {
             if (!overlap) {
                 Scope sc(s, 8);
                 launch_update_lazy((*s->cur), lp.lazy_begin, lp.lazy_end, s->lazy_ctr + 2 * l, s->nsm, 0, st);
             } else {
+                cudaStream_t side = (nbatch % s->nside == 0) ? s->side_stream : s->side2[nbatch % s->nside - 1];
+                nbatch++;
                 CK(cudaEventRecord(s->ev_f[l], st));
-                CK(cudaStreamWaitEvent(s->side_stream, s->ev_f[l], 0));
-                launch_update_lazy((*s->cur), lp.lazy_begin, lp.lazy_end, s->lazy_ctr + 2 * l, s->nsm, s->chain_sms, s->side_stream);
-                CK(cudaEventRecord(s->ev_lazy[l], s->side_stream));
-                last_lazy = (long)l;
+                CK(cudaStreamWaitEvent(side, s->ev_f[l], 0));
+                if (split) CK(cudaStreamWaitEvent(side, s->ev_tr[l], 0));
+                const bool late = s->chain_sms_late >= 0 && (double)l >= s->chain_switch * (double)nlev;
+                launch_update_lazy((*s->cur), lp.lazy_begin, lp.lazy_end, s->lazy_ctr + 2 * l, s->nsm, late ? s->chain_sms_late : s->chain_sms, side);
+                CK(cudaEventRecord(s->ev_lazy[l], side));
                 has_lazy[l] = 1;
             }
             count++;
         }
-        if (lp.ext_end > lp.ext_begin) { Scope sc(s, 4); launch_update((*s->cur), lp.ext_begin, lp.ext_end, 1, st); count++; }
+        if ((long)l == pack_level && lp.pack_end > 0) {
+            cudaStream_t ps = s->side2[2];
+            if (!(lp.lazy_end > lp.lazy_begin)) CK(cudaEventRecord(s->ev_f[l], st));
+            CK(cudaStreamWaitEvent(ps, s->ev_f[l], 0));
+            if (split) CK(cudaStreamWaitEvent(ps, s->ev_tr[l], 0));
+            launch_invert_diag((*s->cur), 0, lp.inv_end, ps);
+            launch_pack_big((*s->cur), 0, lp.pack_end, ps);
+            CK(cudaEventRecord(s->ev_pack, ps));
+            inv_done = lp.inv_end;
+            pack_done = lp.pack_end;
+            early_pack = true;
+            count += 2;
+        }
+        if (!split) {
+            if (lp.ext_end > lp.ext_begin) { Scope sc(s, 4); launch_update((*s->cur), lp.ext_begin, lp.ext_end, 1, st); count++; }
+        } else {
+            if (!(lp.lazy_end > lp.lazy_begin) && (long)l != pack_level) CK(cudaEventRecord(s->ev_f[l], st));   // critical trsm done
+            CK(cudaStreamWaitEvent(s->aux_stream, s->ev_f[l], 0));
+            if (lp.ext_end > lp.ext_crit_end) { launch_update((*s->cur), lp.ext_crit_end, lp.ext_end, 1, s->aux_stream); count++; }
+            CK(cudaEventRecord(s->ev_ur[l], s->aux_stream));
+            if (lp.ext_crit_end > lp.ext_begin) { launch_update((*s->cur), lp.ext_begin, lp.ext_crit_end, 1, st); count++; }
+        }
     }
-    if (overlap && last_lazy > waited) CK(cudaStreamWaitEvent(st, s->ev_lazy[last_lazy], 0));   // join
-    if ((*s->cur).ndblk > 0) { Scope sc(s, 10); launch_invert_diag((*s->cur), st); count++; }
-    if (!s->plan.big_pack.empty()) { Scope sc(s, 13); launch_pack_big((*s->cur), 0, (int32_t)s->plan.big_pack.size(), st); count++; }
+    if (overlap && s->split_chain && nlev > 0) CK(cudaStreamWaitEvent(st, s->ev_ur[nlev - 1], 0));
+    if (overlap)
+        for (long q = waited + 1; q < (long)nlev; ++q)
+            if (has_lazy[q]) CK(cudaStreamWaitEvent(st, s->ev_lazy[q], 0));   // join
+    if (early_pack) CK(cudaStreamWaitEvent(st, s->ev_pack, 0));
+    if ((*s->cur).ndblk > inv_done) { Scope sc(s, 10); launch_invert_diag((*s->cur), inv_done, (*s->cur).ndblk, st); count++; }
+    if ((int32_t)s->plan.big_pack.size() > pack_done) { Scope sc(s, 13); launch_pack_big((*s->cur), pack_done, (int32_t)s->plan.big_pack.size(), st); count++; }
     if (s->dc.nd > 0) {
         // V = K_s^{-1} A_d : one sparse solve per dense column, then the nd x nd Schur matrix and its Cholesky factor
         Scope sc(s, 12);
@@ -467,6 +526,12 @@ void setup_device(tlpb200_solver* s) {
         CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         CK(cudaStreamCreateWithPriority(&s->own_stream, cudaStreamNonBlocking, hi));
         CK(cudaStreamCreateWithPriority(&s->side_stream, cudaStreamNonBlocking, lo));
+        for (auto& x : s->side2) CK(cudaStreamCreateWithPriority(&x, cudaStreamNonBlocking, lo));
+        CK(cudaStreamCreateWithPriority(&s->aux_stream, cudaStreamNonBlocking, std::min(lo, hi + 1)));
+        if (const char* e = getenv("TLPB200_SPLIT_CHAIN")) s->split_chain = atoi(e) != 0;
+        if (const char* e = getenv("TLPB200_PACK_SPLIT")) s->pack_split = atof(e);
+        CK(cudaEventCreateWithFlags(&s->ev_pack, cudaEventDisableTiming));
+        if (const char* e = getenv("TLPB200_SIDE_STREAMS")) s->nside = std::max(1, std::min(4, atoi(e)));
     }
     s->stream = s->own_stream;
     CK(kernels_static_init());
@@ -501,6 +566,7 @@ void setup_device(tlpb200_solver* s) {
     c.sn_dblk = upload(s, P.sn_dblk);
     c.dblk_sn = upload(s, P.dblk_sn);
     c.dblk_idx = upload(s, P.dblk_idx);
+    c.inv_order = upload(s, P.inv_order);
     c.ndblk = P.ndblk;
     c.has_neg = (s->system == TLPB200_K2) ? 1 : 0;
     c.Lx = dalloc<double>(s, (size_t)S.lx_size);
@@ -547,6 +613,8 @@ void setup_device(tlpb200_solver* s) {
     }
     s->nsm = prop.multiProcessorCount;
     if (const char* e = getenv("TLPB200_CHAIN_SMS")) s->chain_sms = std::max(0, std::min(s->nsm - 1, atoi(e)));
+    if (const char* e = getenv("TLPB200_CHAIN_SMS_LATE")) s->chain_sms_late = std::max(0, std::min(s->nsm - 1, atoi(e)));
+    if (const char* e = getenv("TLPB200_CHAIN_SWITCH")) s->chain_switch = atof(e);
 
     DevMat& A = s->mat;
     A.m = s->m; A.n = s->n; A.nnz = s->nnz;
@@ -1133,6 +1201,12 @@ void tlpb200_destroy(tlpb200_solver* s) {
         for (auto& ev : s->ev_f) cudaEventDestroy(ev);
         for (auto& ev : s->ev_lazy) cudaEventDestroy(ev);
         if (s->side_stream) cudaStreamDestroy(s->side_stream);
+        for (auto& x : s->side2) if (x) cudaStreamDestroy(x);
+        if (s->aux_stream) cudaStreamDestroy(s->aux_stream);
+        if (s->ev_pack) cudaEventDestroy(s->ev_pack);
+        for (auto& ev : s->ev_d) cudaEventDestroy(ev);
+        for (auto& ev : s->ev_tr) cudaEventDestroy(ev);
+        for (auto& ev : s->ev_ur) cudaEventDestroy(ev);
         if (s->own_stream) cudaStreamDestroy(s->own_stream);
     }
     delete s;
