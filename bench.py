@@ -268,13 +268,27 @@ def gpu_arm(args):
                 "peak_source": "cuBLAS DGEMM 4096^3 measured live in this run (MEASURED_PEAKS.json has no FP64 figure; nominal B200 FP64 = 40 TFLOP/s)",
                 "launches_per_step": int(n_upd), "avg_launch_ms": round(ms_upd / max(1, n_upd), 4),
                 "algorithmic_flops_per_step": flops_upd, "share_of_update_ms": round(ms_upd / max(1e-9, sp["ms_assemble"] + sp["ms_factor"]), 3)}
-    solve_bytes = 16.0 * sp["nnzL_stored"] if sp["nnzL_stored"] else 0.0
     ms_tri = sum(cls[k][0] for k in ("fwd_small", "fwd_large", "bwd_large", "bwd_small", "fwd_big", "bwd_big"))
-    roofline_solve = {"kernel": "supernodal forward+backward sweep (one rhs): k_fwd_big + k_bwd_big (+ small/medium supernode kernels)", "bound": "hbm",
-                      "achieved": round(16.0 * sp["nnzL"] / (ms_tri * 1e-3) / 1e9, 1) if ms_tri > 0 else None,
-                      "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
-                      "frac": round(16.0 * sp["nnzL"] / (ms_tri * 1e-3) / 1e9 / peaks["hbm_gbs"], 4) if ms_tri > 0 else None,
-                      "algorithmic_bytes": 16.0 * sp["nnzL"], "stored_bytes_read": solve_bytes, "ms": round(ms_tri, 3),
+    # dominant solve kernels: the dense sweeps over the big supernodes (k_fwd_big + k_bwd_big); their algorithmic
+    # bytes are 16 B per non-zero of the big supernodes' panels (L read once forward, once backward: SURVEY 8d)
+    bp = kkt.big_plan()
+    sym = kkt.symbolic()
+    big_sn = np.unique(bp["fwd"]["sn"]) if len(bp["fwd"]) else np.zeros(0, np.int64)
+    nc_b = (sym["sn_first"][big_sn + 1] - sym["sn_first"][big_sn]).astype(np.float64)
+    nr_b = (sym["sn_rowptr"][big_sn + 1] - sym["sn_rowptr"][big_sn]).astype(np.float64)
+    nnz_big = float(np.sum(nc_b * nr_b - nc_b * (nc_b - 1) / 2))
+    ms_big = cls["fwd_big"][0] + cls["bwd_big"][0]
+    ach_big = 16.0 * nnz_big / (ms_big * 1e-3) / 1e9 if ms_big > 0 else None
+    roofline_solve = {"kernel": "k_fwd_big + k_bwd_big (dense sweeps over the big supernodes, one rhs)", "bound": "hbm",
+                      "achieved": round(ach_big, 1) if ach_big else None, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                      "frac": round(ach_big / peaks["hbm_gbs"], 4) if ach_big else None,
+                      "algorithmic_bytes": 16.0 * nnz_big, "ms": round(ms_big, 4), "launches_per_solve": int(cls["fwd_big"][1] + cls["bwd_big"][1]),
+                      "streamed_tile_bytes": (bp["n_ftiles"] + bp["n_btiles"]) * 128 * 128 * 8,
+                      "share_of_L": round(nnz_big / max(1.0, float(sp["nnzL"])), 4),
+                      "whole_sweep": {"ms": round(ms_tri, 4), "algorithmic_bytes": 16.0 * sp["nnzL"],
+                                      "achieved": round(16.0 * sp["nnzL"] / (ms_tri * 1e-3) / 1e9, 1) if ms_tri > 0 else None,
+                                      "frac": round(16.0 * sp["nnzL"] / (ms_tri * 1e-3) / 1e9 / peaks["hbm_gbs"], 4) if ms_tri > 0 else None,
+                                      "note": "all sweep kernels of one solve (small / medium / below / big), CUDA-event brackets per launch"},
                       "peak_source": peak_src}
     phases = {k: {"ms": round(v[0], 4), "launches": int(v[1])} for k, v in cls.items()}
     out = {

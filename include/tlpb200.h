@@ -132,6 +132,10 @@ int tlpb200_debug_get_lx(tlpb200_solver* s, double* lx, int64_t* xptr /* nsuper+
 /* globaltimer (ns) of every block publish of the last dense sweeps: out[0..nblk) forward, out[nblk..2 nblk) backward;
    recorded only when TLPB200_CHAIN_TIMES was set in the environment at tlpb200_create */
 int tlpb200_debug_chain_times(tlpb200_solver* s, uint64_t* out, int64_t* nblk);
+/* factorisation timeline of the last update! (needs TLPB200_TRACE_FACTOR in the environment at tlpb200_create):
+   out[level][cls][2] = globaltimer ns of the first CTA start / last CTA end of cls = {diagonal blocks, trsm, urgent update
+   tiles, lazy update tiles}; zeros where a class is absent */
+int tlpb200_debug_factor_trace(tlpb200_solver* s, uint64_t* out, int64_t* nlevels);
 int tlpb200_debug_big_plan(const tlpb200_solver* s, int64_t* counts, void* pack, void* fwd, void* bwd);
 
 /* ---- multi-GPU, one process per GPU (no counterpart in the reference, NEWS.md:31) -------------

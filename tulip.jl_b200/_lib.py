@@ -60,7 +60,7 @@ SYMBOLS = [
     "tlpb200_backend_name", "tlpb200_linear_system", "tlpb200_destroy",
     "tlpb200_dist_info", "tlpb200_update_begin", "tlpb200_top_panels", "tlpb200_update_end",
     "tlpb200_solve_begin", "tlpb200_work_vector", "tlpb200_solve_mid", "tlpb200_solve_end",
-    "tlpb200_get_dense_cols", "tlpb200_debug_big_plan", "tlpb200_debug_chain_times",
+    "tlpb200_get_dense_cols", "tlpb200_debug_big_plan", "tlpb200_debug_chain_times", "tlpb200_debug_factor_trace",
 ]
 
 _lib = None
@@ -112,6 +112,8 @@ def load():
     lib.tlpb200_debug_big_plan.restype = C.c_int
     lib.tlpb200_debug_chain_times.argtypes = [p, p, C.POINTER(C.c_int64)]
     lib.tlpb200_debug_chain_times.restype = C.c_int
+    lib.tlpb200_debug_factor_trace.argtypes = [p, p, C.POINTER(C.c_int64)]
+    lib.tlpb200_debug_factor_trace.restype = C.c_int
     lib.tlpb200_last_error.argtypes = [p]
     lib.tlpb200_last_error.restype = C.c_char_p
     lib.tlpb200_backend_name.argtypes = []

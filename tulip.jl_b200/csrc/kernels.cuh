@@ -56,11 +56,24 @@ struct DevCtx {
     unsigned long long* epoch;     // [0] sweep counter (bumped by the last CTA of every dense sweep), [1] exit counter
     unsigned long long* dbg_ts;    // [2 * nxblk] globaltimer at every block publish (forward, then backward); nullptr = off
     int32_t nxblk;                 // xq_slots / 128
+    unsigned long long* trace_min; // [nlevels][4] first CTA start of {diag, trsm, urgent update, lazy update} (nullptr = off)
+    unsigned long long* trace_max; // [nlevels][4] last CTA end
     const BelowItem* bwd_below;
     const int32_t* sn_split;       // [nsuper] 1 = rows below the columns are accumulated into bacc by k_bwd_below
     double* bacc;                  // [N] backward accumulator sum_rows L[row, c] x[row]; consumers re-zero their entries
     const int8_t* skip;   // multi-GPU: skip[s] != 0 -> supernode s is not processed in this phase on this rank (nullptr: none)
 };
+
+#ifdef __CUDACC__
+// factorisation timeline (TLPB200_TRACE_FACTOR): per level and kernel class, globaltimer of the first start / last end
+__device__ __forceinline__ void trace_mark(const DevCtx& c, int level, int cls, bool end) {
+    if (!c.trace_min) return;
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+    if (end) atomicMax(c.trace_max + 4 * level + cls, t);
+    else atomicMin(c.trace_min + 4 * level + cls, t);
+}
+#endif
 
 // matrix A on the device (CSC + CSR copies) and the assemble maps
 struct DevMat {

@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(DF_THREADS, 1) k_diag_factor(DevCtx c, int32_t
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int il = tid & (PIECE - 1), q4 = tid >> 7;
 
+    if (tid == 0) trace_mark(c, pc.level, 0, false);
     if (tid < w) sgn[tid] = (double)c.sign[pc.c0 + tid];
     for (int kb = 0; kb < w; kb += 32) {       // 8 independent loads in flight per thread
         double v[8];
@@ -205,6 +206,7 @@ __global__ void __launch_bounds__(DF_THREADS, 1) k_diag_factor(DevCtx c, int32_t
     __syncthreads();
     for (int k = q4; k < w; k += 4)
         if (il < w && il >= k) D[(int64_t)k * ld + il] = (il == k) ? dd[k] : Cs[k * LDD + il] * rdd[k];
+    if (tid == 0) trace_mark(c, pc.level, 0, true);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -237,6 +239,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_trsm(DevCtx c, int32_t begin)
     const double* L11 = X + (int64_t)kb * ld + kb;
     const int8_t* sgn = c.sign + pc.c0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t4 = lane & 3;
+    if (tid == 0) trace_mark(c, pc.level, 1, false);
     const int nblk = (w + TRB - 1) / TRB;
 
     for (int b = 0; b < nblk; ++b) {
@@ -300,6 +303,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_trsm(DevCtx c, int32_t begin)
         }
         __syncthreads();
     }
+    if (tid == 0) trace_mark(c, pc.level, 1, true);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -325,10 +329,11 @@ struct UpdShared {
     int32_t next;
 };
 
-__device__ __forceinline__ void update_tile(const DevCtx& c, const UpdTask& T, double* smem_d, UpdShared& sh, int atomic) {
+__device__ __forceinline__ void update_tile(const DevCtx& c, const UpdTask& T, double* smem_d, UpdShared& sh, int atomic, int cls) {
     const Piece pc = c.pieces[T.piece];
     const int32_t s = pc.sn;
     if (c.skip && c.skip[s]) return;     // uniform per CTA
+    if (threadIdx.x == 0) trace_mark(c, pc.level, cls, false);
     const int32_t f = c.sn_first[s];
     const int64_t rp = c.sn_rowptr[s];
     const int32_t ld = (int32_t)(c.sn_rowptr[s + 1] - rp);
@@ -420,13 +425,14 @@ __device__ __forceinline__ void update_tile(const DevCtx& c, const UpdTask& T, d
                     if (atomic) atomicAdd(p, -acc[mi][nj][e]); else *p -= acc[mi][nj][e];
                 }
             }
+    if (threadIdx.x == 0) trace_mark(c, pc.level, cls, true);
 }
 
 __global__ void __launch_bounds__(UPD_THREADS, 4) k_update(DevCtx c, int32_t begin, int atomic) {
     extern __shared__ double smem_d[];
     __shared__ UpdShared sh;
     const UpdTask T = c.upd[begin + blockIdx.x];
-    update_tile(c, T, smem_d, sh, atomic);
+    update_tile(c, T, smem_d, sh, atomic, 2);
 }
 
 __global__ void __launch_bounds__(UPD_THREADS, 4) k_update_lazy(DevCtx c, int32_t begin, int32_t end, int32_t* counter,
@@ -448,7 +454,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 4) k_update_lazy(DevCtx c, int32_
         const int32_t task = sh.next;
         if (task >= end) return;
         const UpdTask T = c.upd_lazy[task];
-        update_tile(c, T, smem_d, sh, 1);
+        update_tile(c, T, smem_d, sh, 1, 3);
         cp_async_wait_<0>();
         __syncthreads();       // shared state is reused by the next tile
     }

@@ -46,7 +46,9 @@ struct tlpb200_solver {
     cudaStream_t aux_stream = nullptr;        // non-critical part of the chain kernels (TLPB200_SPLIT_CHAIN)
     bool split_chain = true;
     cudaEvent_t ev_pack = nullptr;
-    double pack_split = 0.55;     // TLPB200_PACK_SPLIT: level fraction at which the early invert/repack batch is issued (0 = off)
+    int pack_slice = 96;          // TLPB200_PACK_SLICE: repack tiles issued per level from the split level on
+    double pack_split = 0.0;      // TLPB200_PACK_SPLIT: level fraction from which invert/repack slices are issued early (0 = off:
+                                  // measured no gain on cfg2 -- the slices queue behind the 250 us diagonal-block inversions)
 
     std::vector<void*> allocs;
     size_t bytes_device = 0;
@@ -176,6 +178,10 @@ void enqueue_assemble(tlpb200_solver* s, int64_t& count) {
     CK(cudaMemsetAsync(s->ctx.Lx, 0, (size_t)s->sym.lx_size * sizeof(double), st));
     CK(cudaMemsetAsync(s->ctx.info, 0x7f, sizeof(int32_t), st));
     CK(cudaMemsetAsync(s->lazy_ctr, 0, (2 * s->plan.levels.size() + 2) * sizeof(int32_t), st));
+    if (s->ctx.trace_min) {
+        CK(cudaMemsetAsync(s->ctx.trace_min, 0xff, 4 * s->plan.levels.size() * sizeof(unsigned long long), st));
+        CK(cudaMemsetAsync(s->ctx.trace_max, 0, 4 * s->plan.levels.size() * sizeof(unsigned long long), st));
+    }
     if (s->system == TLPB200_K1) {
         launch_compute_d(s->d_theta, s->d_regP, s->d_d, s->n, st);
         launch_assemble_k1(s->ctx, s->mat, s->d_d, s->d_regD, st);
@@ -236,6 +242,7 @@ void enqueue_factor(tlpb200_solver* s, int64_t& count) {
         }
         if (lp.piece_end > lp.piece_begin) { Scope sc(s, 2); launch_diag_factor((*s->cur), lp.piece_begin, lp.piece_end, st); count++; }
         const bool split = overlap && s->split_chain;
+        bool ev_f_recorded = false;
         if (!split) {
             if (lp.panel_end > lp.panel_begin) { Scope sc(s, 3); launch_trsm((*s->cur), lp.panel_begin, lp.panel_end, st); count++; }
         } else {
@@ -267,23 +274,24 @@ void enqueue_factor(tlpb200_solver* s, int64_t& count) {
             }
             count++;
         }
-        if ((long)l == pack_level && lp.pack_end > 0) {
+        if (pack_level >= 0 && (long)l >= pack_level && (lp.pack_end > pack_done || lp.inv_end > inv_done)) {
+            // a slice of the invert / repack work per level: short-lived CTAs that fill idle SMs of the tail without
+            // holding them against the chain kernels
             cudaStream_t ps = s->side2[2];
             if (!(lp.lazy_end > lp.lazy_begin)) CK(cudaEventRecord(s->ev_f[l], st));
             CK(cudaStreamWaitEvent(ps, s->ev_f[l], 0));
             if (split) CK(cudaStreamWaitEvent(ps, s->ev_tr[l], 0));
-            launch_invert_diag((*s->cur), 0, lp.inv_end, ps);
-            launch_pack_big((*s->cur), 0, lp.pack_end, ps);
+            if (lp.inv_end > inv_done) { launch_invert_diag((*s->cur), inv_done, lp.inv_end, ps); inv_done = lp.inv_end; count++; }
+            const int32_t pe = std::min(lp.pack_end, pack_done + s->pack_slice);
+            if (pe > pack_done) { launch_pack_big((*s->cur), pack_done, pe, ps); pack_done = pe; count++; }
             CK(cudaEventRecord(s->ev_pack, ps));
-            inv_done = lp.inv_end;
-            pack_done = lp.pack_end;
             early_pack = true;
-            count += 2;
+            ev_f_recorded = true;
         }
         if (!split) {
             if (lp.ext_end > lp.ext_begin) { Scope sc(s, 4); launch_update((*s->cur), lp.ext_begin, lp.ext_end, 1, st); count++; }
         } else {
-            if (!(lp.lazy_end > lp.lazy_begin) && (long)l != pack_level) CK(cudaEventRecord(s->ev_f[l], st));   // critical trsm done
+            if (!(lp.lazy_end > lp.lazy_begin) && !ev_f_recorded) CK(cudaEventRecord(s->ev_f[l], st));   // critical trsm done
             CK(cudaStreamWaitEvent(s->aux_stream, s->ev_f[l], 0));
             if (lp.ext_end > lp.ext_crit_end) { launch_update((*s->cur), lp.ext_crit_end, lp.ext_end, 1, s->aux_stream); count++; }
             CK(cudaEventRecord(s->ev_ur[l], s->aux_stream));
@@ -530,6 +538,7 @@ void setup_device(tlpb200_solver* s) {
         CK(cudaStreamCreateWithPriority(&s->aux_stream, cudaStreamNonBlocking, std::min(lo, hi + 1)));
         if (const char* e = getenv("TLPB200_SPLIT_CHAIN")) s->split_chain = atoi(e) != 0;
         if (const char* e = getenv("TLPB200_PACK_SPLIT")) s->pack_split = atof(e);
+        if (const char* e = getenv("TLPB200_PACK_SLICE")) s->pack_slice = std::max(1, atoi(e));
         CK(cudaEventCreateWithFlags(&s->ev_pack, cudaEventDisableTiming));
         if (const char* e = getenv("TLPB200_SIDE_STREAMS")) s->nside = std::max(1, std::min(4, atoi(e)));
     }
@@ -587,6 +596,11 @@ void setup_device(tlpb200_solver* s) {
     CK(cudaMemset(c.bacc, 0, std::max<size_t>(S.N, 1) * sizeof(double)));
     c.xq = dalloc<unsigned long long>(s, (size_t)2 * P.xq_slots);
     CK(cudaMemset(c.xq, 0, std::max<size_t>(2 * (size_t)P.xq_slots, 1) * sizeof(unsigned long long)));
+    c.trace_min = c.trace_max = nullptr;
+    if (getenv("TLPB200_TRACE_FACTOR")) {
+        c.trace_min = dalloc<unsigned long long>(s, 4 * P.levels.size());
+        c.trace_max = dalloc<unsigned long long>(s, 4 * P.levels.size());
+    }
     c.nxblk = P.xq_slots / SBLK;
     c.dbg_ts = nullptr;
     if (getenv("TLPB200_CHAIN_TIMES")) {
@@ -1000,6 +1014,25 @@ int tlpb200_debug_chain_times(tlpb200_solver* s, uint64_t* out, int64_t* nblk) {
     if (!s->ctx.dbg_ts) return fail(s, TLPB200_BAD_ARG, "chain times were not recorded (TLPB200_CHAIN_TIMES unset at setup)");
     cudaStreamSynchronize(s->stream);
     if (out) cudaMemcpy(out, s->ctx.dbg_ts, (size_t)2 * s->ctx.nxblk * sizeof(uint64_t), cudaMemcpyDeviceToHost);
+    return TLPB200_OK;
+}
+
+/* factorisation timeline of the last update! (TLPB200_TRACE_FACTOR set at create): out[level][cls][0/1] = globaltimer ns of
+   the first CTA start / last CTA end of cls = {diag, trsm, urgent update, lazy update}; 0 = class absent at that level */
+int tlpb200_debug_factor_trace(tlpb200_solver* s, uint64_t* out, int64_t* nlevels) {
+    REQUIRE_DEVICE(s);
+    const size_t nl = s->plan.levels.size();
+    if (nlevels) *nlevels = (int64_t)nl;
+    if (!s->ctx.trace_min) return fail(s, TLPB200_BAD_ARG, "factor trace was not recorded (TLPB200_TRACE_FACTOR unset at setup)");
+    if (!out) return TLPB200_OK;
+    cudaStreamSynchronize(s->stream);
+    std::vector<unsigned long long> mn(4 * nl), mx(4 * nl);
+    cudaMemcpy(mn.data(), s->ctx.trace_min, mn.size() * 8, cudaMemcpyDeviceToHost);
+    cudaMemcpy(mx.data(), s->ctx.trace_max, mx.size() * 8, cudaMemcpyDeviceToHost);
+    for (size_t i = 0; i < 4 * nl; ++i) {
+        out[2 * i] = (mx[i] == 0) ? 0 : mn[i];
+        out[2 * i + 1] = mx[i];
+    }
     return TLPB200_OK;
 }
 

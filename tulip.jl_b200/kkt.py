@@ -287,6 +287,18 @@ class B200KKTSolver:
             _raise(rc, self._h)
         return out[:nb.value].astype(np.int64), out[nb.value:].astype(np.int64)
 
+    def factor_trace(self):
+        """[nlevels, 4, 2] globaltimer ns (first start, last end) of {diag, trsm, urgent, lazy} per level of the last
+        update! (needs TLPB200_TRACE_FACTOR=1 in the environment at setup)."""
+        lib = _lib.load()
+        nl = C.c_int64(0)
+        lib.tlpb200_debug_factor_trace(self._h, None, C.byref(nl))
+        out = np.zeros((nl.value, 4, 2), np.uint64)
+        rc = lib.tlpb200_debug_factor_trace(self._h, C.c_void_p(out.ctypes.data), C.byref(nl))
+        if rc != _lib.OK:
+            _raise(rc, self._h)
+        return out.astype(np.int64)
+
     def big_plan(self):
         """Dense-solve plan of the big supernodes (host data, available on analyze_only handles)."""
         lib = _lib.load()
