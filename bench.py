@@ -274,9 +274,11 @@ def gpu_arm(args):
     bp = kkt.big_plan()
     sym = kkt.symbolic()
     big_sn = np.unique(bp["fwd"]["sn"]) if len(bp["fwd"]) else np.zeros(0, np.int64)
-    nc_b = (sym["sn_first"][big_sn + 1] - sym["sn_first"][big_sn]).astype(np.float64)
-    nr_b = (sym["sn_rowptr"][big_sn + 1] - sym["sn_rowptr"][big_sn]).astype(np.float64)
-    nnz_big = float(np.sum(nc_b * nr_b - nc_b * (nc_b - 1) / 2))
+    # structural non-zeros of those supernodes' columns (exact column counts: the panels also hold the explicit zeros
+    # of relaxed amalgamation, which are streamed but are not algorithmic bytes)
+    cc = np.asarray(sym["colcount"], dtype=np.float64)
+    csum = np.concatenate([[0.0], np.cumsum(cc)])
+    nnz_big = float(np.sum(csum[sym["sn_first"][big_sn + 1]] - csum[sym["sn_first"][big_sn]]))
     ms_big = cls["fwd_big"][0] + cls["bwd_big"][0]
     ach_big = 16.0 * nnz_big / (ms_big * 1e-3) / 1e9 if ms_big > 0 else None
     roofline_solve = {"kernel": "k_fwd_big + k_bwd_big (dense sweeps over the big supernodes, one rhs)", "bound": "hbm",
@@ -369,6 +371,41 @@ def sharded_arm(args, pkg, lp, sysname, sy, dist, rank, world, local):
         print(json.dumps(out), flush=True)
 
 
+EXTRAPOLATE_ABOVE_FLOPS = 5e12     # one CPU factorisation beyond this does not fit a bounded sample
+
+
+def cpu_sample_extrapolated(st, nsolve):
+    """Bounded CPU sample for a dense-dominated config whose CPU factorisation takes minutes to hours (config T:
+    SURVEY 8d option A): time the two dense kernels that carry > 99 % of the CPU port's work on this workload -- LAPACK
+    dpotrf and the triangular solves, SciPy's OpenBLAS, all host cores -- on an n0 x n0 block, and scale by the
+    factorisation's flop count sum_j c_j^2 and the solves' 16 nnz(L) bytes.  Labelled as an extrapolation."""
+    import scipy.linalg as sla
+    cores = os.cpu_count() or 1
+    n0 = 12000
+    rng = np.random.default_rng(0)
+    M = rng.standard_normal((n0, 64))
+    S = np.asfortranarray(M @ M.T)
+    S[np.diag_indices(n0)] += 64.0
+    t0 = time.perf_counter()
+    L, info = sla.lapack.dpotrf(S, lower=1, overwrite_a=1)
+    t_f = time.perf_counter() - t0
+    rate = n0 ** 3 / 3.0 / t_f                      # flops/s in the c_j^2 convention (sum_j c_j^2 = n^3/3 when dense)
+    x = rng.standard_normal(n0)
+    t0 = time.perf_counter()
+    reps = 5
+    for _ in range(reps):
+        y = sla.solve_triangular(L, x, lower=True, check_finite=False)
+        y = sla.solve_triangular(L, y, lower=True, trans=1, check_finite=False)
+    t_s = (time.perf_counter() - t0) / reps
+    bw = 16.0 * (n0 * (n0 + 1) / 2) / t_s           # algorithmic bytes/s of one forward+backward solve
+    t_iter = st["flops"] / rate + nsolve * 16.0 * st["nnzL"] / bw
+    return {"value": round(1.0 / t_iter, 6), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"EXTRAPOLATED (a full CPU factorisation of this config takes ~{st['flops'] / rate / 60:.0f} min): dense dpotrf "
+                      f"{n0}^2 in {t_f:.1f} s = {rate / 1e9:.0f} GF/s (c_j^2 convention) and forward+backward solve at {bw / 1e9:.1f} GB/s, "
+                      f"scaled to sum c_j^2 = {st['flops']:.3e} flops + {nsolve:.2f} solves x 16 nnz(L) = {16.0 * st['nnzL'] / 1e9:.1f} GB",
+            "label": "CPU port kernels (SciPy-OpenBLAS dpotrf / dtrsv, all host cores) -- NOT Tulip/CHOLMOD; not run to completion"}
+
+
 def cpu_sample(pkg, lp, sysname, rec):
     """oracle CPU port on a bounded sample: ONE recorded IPM iteration (1 update! + its solves)."""
     from oracle import cpu_kkt
@@ -377,6 +414,9 @@ def cpu_sample(pkg, lp, sysname, rec):
     sy = pkg.K1() if sysname == "K1" else pkg.K2()
     an = pkg.setup(A, sy, pkg.Backend(analyze_only=True))
     cores = os.cpu_count() or 1
+    st = an.stats()
+    if st["flops"] > EXTRAPOLATE_ABOVE_FLOPS:
+        return cpu_sample_extrapolated(st, float(len(rec["rhs"])))
     ck = cpu_kkt.CpuSupernodalKKT(A, sysname, nthreads=cores, symbolic_from=an)
     t0 = time.perf_counter()
     ck.update(rec["theta"], rec["regP"], rec["regD"])
@@ -404,6 +444,16 @@ def reference_arm(args):
     sy = pkg.K1() if sysname == "K1" else pkg.K2()
     an = pkg.setup(A, sy, pkg.Backend(analyze_only=True))       # integer analysis only, no device
     cores = os.cpu_count() or 1
+    st = an.stats()
+    if st["flops"] > EXTRAPOLATE_ABOVE_FLOPS:
+        nsolve = 5.0
+        cb = cpu_sample_extrapolated(st, nsolve)
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": world,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 / cb["value"], 1),
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                          "config": {"workload": workload_name(lp, sysname, nsolve)}, "cpu_baseline": cb,
+                          "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+        return
     ck = cpu_kkt.CpuSupernodalKKT(A, sysname, nthreads=cores, symbolic_from=an)
     K, W = args.steps, args.warmup
     marks = []
