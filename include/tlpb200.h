@@ -54,9 +54,13 @@ typedef struct tlpb200_options {
                                     0 = auto (max(32, 5% of m)), < 0 = off */
     int32_t dense_solve_ncol;    /* non-small supernodes with at least this many columns use the dense-solve path
                                     (repacked unit-block-diagonal tiles, flag-in-data hand-over); 0 = default (384) */
-    int32_t reserved[5];
+    int32_t ozaki_ncol;          /* K1, single GPU: supernodes with at least this many columns run their far Schur updates on
+                                    the tcgen05 int8 tensor-core path (exact digit-plane products, FP64-grade result);
+                                    0 = default (1024), < 0 = off (FP64 DMMA path everywhere) */
+    int32_t reserved[4];
 } tlpb200_options;
 
+#define TLPB200_NCLASS 24
 typedef struct tlpb200_stats {
     int64_t m, n, nnzA;
     int64_t order;          /* N: m for K1, n+m for K2 */
@@ -78,8 +82,11 @@ typedef struct tlpb200_stats {
     /* profiling mode: CUDA-event time and launch count per kernel class of the last update!/solve!
      * 0 assemble  1 small_factor  2 diag_factor  3 trsm  4 update  5 rhs+recover
      * 6 fwd_small 7 fwd_large 8 -  9 bwd_large 10 invert_diag 11 bwd_small */
-    double ms_class[16];
-    int64_t n_class[16];
+    double ms_class[TLPB200_NCLASS];   /* ... 12 dense_cols 13 pack_big 14 fwd_big 15 bwd_big 16 oz_slice 17 oz_update */
+    int64_t n_class[TLPB200_NCLASS];
+    double flops_update_oz; /* algorithmic flops of one update! done by the tcgen05 int8 tasks (not part of flops_update_ext) */
+    int64_t oz_tasks;       /* tcgen05 tasks per update! */
+    int64_t oz_bytes;       /* device bytes of the digit planes */
 } tlpb200_stats;
 
 void tlpb200_default_options(tlpb200_options* opt);
@@ -136,6 +143,10 @@ int tlpb200_debug_chain_times(tlpb200_solver* s, uint64_t* out, int64_t* nblk);
    out[level][cls][2] = globaltimer ns of the first CTA start / last CTA end of cls = {diagonal blocks, trsm, urgent update
    tiles, lazy update tiles}; zeros where a class is absent */
 int tlpb200_debug_factor_trace(tlpb200_solver* s, uint64_t* out, int64_t* nlevels);
+/* Stand-alone check of the tcgen05 int8 (Ozaki) Schur-update path on a dense matrix: C (R x R, column-major, lower part)
+ * -= P P' with P R x K column-major; `ksplit` = K columns per task (multiple of 32, 0 = all).  ms[0] = digit-plane
+ * kernels, ms[1] = one update pass (mean of `reps`), ms[2] = tasks; *err != 0 = pipeline time-out. */
+int tlpb200_debug_ozaki(const double* P, int64_t R, int64_t K, double* C, int32_t ksplit, int32_t reps, float* ms, int32_t* err);
 int tlpb200_debug_big_plan(const tlpb200_solver* s, int64_t* counts, void* pack, void* fwd, void* bwd);
 
 /* ---- multi-GPU, one process per GPU (no counterpart in the reference, NEWS.md:31) -------------

@@ -22,7 +22,7 @@ class Options(C.Structure):
                 ("small_elems", C.c_int32), ("relax_always", C.c_int32), ("use_graph", C.c_int32),
                 ("analyze_only", C.c_int32), ("rank", C.c_int32), ("nranks", C.c_int32),
                 ("dense_col_threshold", C.c_int32), ("dense_solve_ncol", C.c_int32),
-                ("reserved", C.c_int32 * 5)]
+                ("ozaki_ncol", C.c_int32), ("reserved", C.c_int32 * 4)]
 
 
 class Stats(C.Structure):
@@ -36,7 +36,8 @@ class Stats(C.Structure):
                 ("bad_pivot", C.c_int64), ("n_update", C.c_int64), ("n_solve", C.c_int64),
                 ("bytes_device", C.c_int64),
                 ("flops_update_inner", C.c_double), ("flops_update_ext", C.c_double),
-                ("ms_class", C.c_double * 16), ("n_class", C.c_int64 * 16)]
+                ("ms_class", C.c_double * 24), ("n_class", C.c_int64 * 24),
+                ("flops_update_oz", C.c_double), ("oz_tasks", C.c_int64), ("oz_bytes", C.c_int64)]
 
     def asdict(self):
         d = {}
@@ -48,7 +49,7 @@ class Stats(C.Structure):
 
 KERNEL_CLASSES = ["assemble", "small_factor", "diag_factor", "trsm", "update", "rhs_recover",
                   "fwd_small", "fwd_large", "update128", "bwd_large", "invert_diag", "bwd_small", "dense_cols",
-                  "pack_big", "fwd_big", "bwd_big"]
+                  "pack_big", "fwd_big", "bwd_big", "oz_slice", "oz_update"]
 
 
 # every symbol include/tlpb200.h declares (tests check that the library exports all of them)
@@ -60,7 +61,7 @@ SYMBOLS = [
     "tlpb200_backend_name", "tlpb200_linear_system", "tlpb200_destroy",
     "tlpb200_dist_info", "tlpb200_update_begin", "tlpb200_top_panels", "tlpb200_update_end",
     "tlpb200_solve_begin", "tlpb200_work_vector", "tlpb200_solve_mid", "tlpb200_solve_end",
-    "tlpb200_get_dense_cols", "tlpb200_debug_big_plan", "tlpb200_debug_chain_times", "tlpb200_debug_factor_trace",
+    "tlpb200_get_dense_cols", "tlpb200_debug_big_plan", "tlpb200_debug_chain_times", "tlpb200_debug_factor_trace", "tlpb200_debug_ozaki",
 ]
 
 _lib = None
@@ -114,6 +115,8 @@ def load():
     lib.tlpb200_debug_chain_times.restype = C.c_int
     lib.tlpb200_debug_factor_trace.argtypes = [p, p, C.POINTER(C.c_int64)]
     lib.tlpb200_debug_factor_trace.restype = C.c_int
+    lib.tlpb200_debug_ozaki.argtypes = [dp, C.c_int64, C.c_int64, dp, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_int32)]
+    lib.tlpb200_debug_ozaki.restype = C.c_int
     lib.tlpb200_last_error.argtypes = [p]
     lib.tlpb200_last_error.restype = C.c_char_p
     lib.tlpb200_backend_name.argtypes = []

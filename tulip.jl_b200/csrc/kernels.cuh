@@ -144,6 +144,28 @@ void launch_k1_recover(const DevCtx& c, const DevMat& A, const double* d, const 
 void launch_k2_rhs(const DevCtx& c, const DevMat& A, const double* xi_p, const double* xi_d, cudaStream_t st);
 void launch_k2_recover(const DevCtx& c, const DevMat& A, double* dx, double* dy, cudaStream_t st);
 
+// ---- Ozaki / tcgen05 int8 path of the big supernodes' Schur updates (kernels_ozaki.cu) -----------
+constexpr int OZ_S = 8;   // 7-bit digit planes per FP64 value
+
+// one dense square part (first `nrows` rows x columns of a big supernode's panel, or a test matrix)
+struct OzView {
+    const uint8_t* planes;    // digit planes: [row block][K chunk of 32][plane][4096 B]
+    const int64_t* rb_off;    // [row blocks + 1] first K-chunk slot of each row block (units of OZ_S * 4096 B)
+    double* C;                // target panel, column-major
+    int64_t ldc;
+    const double* scl;        // [nrows] 2^E_r of every panel row
+    int32_t nrows;            // rows of the panel
+    int32_t ncols;            // columns of the supernode (targets are columns < ncols)
+};
+
+cudaError_t ozaki_static_init();
+void launch_oz_rowexp(const double* Lx, const int64_t* diagpos, const int32_t* grow, int32_t nrows, int32_t* E, double* scl,
+                      cudaStream_t st);
+void launch_oz_slice(const double* panel, int64_t ld, int32_t nrows, int32_t c0, int32_t w, int32_t rb0, int32_t nrb, int32_t kchunk0,
+                     const int32_t* E, const int64_t* rb_off, uint8_t* planes, cudaStream_t st);
+void launch_oz_update(const OzView* views, const OzTask* tasks, int32_t begin, int32_t end, int32_t* counter, int nsm, int reserve,
+                      int32_t* err, cudaStream_t st);
+
 size_t small_factor_smem(int32_t max_elems, int32_t max_nrow);
 cudaError_t kernels_static_init();   // cudaFuncSetAttribute calls
 cudaError_t factor_kernels_static_init();

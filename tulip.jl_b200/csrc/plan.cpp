@@ -9,6 +9,7 @@ namespace tlp {
 namespace {
 inline int32_t sn_ncol(const Symbolic& S, int32_t s) { return S.sn_first[s + 1] - S.sn_first[s]; }
 inline int32_t sn_nrow(const Symbolic& S, int32_t s) { return (int32_t)(S.sn_rowptr[s + 1] - S.sn_rowptr[s]); }
+inline const int32_t* rows_of(const Symbolic& S, int32_t s) { return S.sn_rows.data() + S.sn_rowptr[s]; }
 }  // namespace
 
 int64_t lx_position(const Symbolic& S, int32_t gi, int32_t gk) {
@@ -69,6 +70,14 @@ void build_plan(const Symbolic& S, const PlanOptions& opt, Plan& P) {
     P.seg_tgt.clear();
     P.max_small_elems = 0;
     P.max_small_nrow = 0;
+    P.sn_oz.assign(ns, -1);
+    P.oz_views.clear();
+    P.oz_rb_off.clear();
+    P.oz_slots = 0;
+    P.oz_rows = 0;
+    P.oz_tasks.clear();
+    P.oz_slices.clear();
+    P.flops_oz = 0.0;
 
     // target segments
     for (int32_t s = 0; s < ns; ++s) {
@@ -98,6 +107,29 @@ void build_plan(const Symbolic& S, const PlanOptions& opt, Plan& P) {
         } else {
             const int32_t np = (nc + PIECE - 1) / PIECE;
             if (nc >= opt.big_ncol) P.sn_big[s] = 1;
+            if (opt.oz_ncol > 0 && nc >= opt.oz_ncol && np >= 4) {
+                bool allpos = true;
+                for (int32_t j = S.sn_first[s]; j < S.sn_first[s + 1] && allpos; ++j) allpos = S.sign[j] > 0;
+                for (int32_t q = nc; q < nr && allpos; ++q) allpos = S.sign[rows_of(S, s)[q]] > 0;
+                if (allpos) {
+                    OzViewPlan v;
+                    v.sn = s;
+                    v.nrb = (nr + 127) / 128;
+                    v.ncb = np;
+                    v.off0 = (int64_t)P.oz_rb_off.size();
+                    v.row0 = P.oz_rows;
+                    v.base_level = base;
+                    v.pad = 0;
+                    P.oz_rows += nr;
+                    for (int32_t rb = 0; rb < v.nrb; ++rb) {
+                        P.oz_rb_off.push_back(P.oz_slots);
+                        P.oz_slots += 4 * (int64_t)std::min(rb, np);      // row block rb holds the planes of pieces 0 .. min(rb, ncb) - 1
+                    }
+                    P.oz_rb_off.push_back(P.oz_slots);
+                    P.sn_oz[s] = (int32_t)P.oz_views.size();
+                    P.oz_views.push_back(v);
+                }
+            }
             P.sn_dblk[s] = (int32_t)P.dblk_sn.size();
             for (int32_t k = 0; k < np; ++k) {
                 Piece pc;
@@ -183,10 +215,12 @@ void build_plan(const Symbolic& S, const PlanOptions& opt, Plan& P) {
             const int32_t nrow = sn_nrow(S, s);
             const int32_t* rows = S.sn_rows.data() + S.sn_rowptr[s];
             const size_t before = P.upd.size(), before128 = P.upd128.size();
+            const int32_t ozv = P.sn_oz[s];
             auto emit_range = [&](int32_t kb, int32_t ke, int32_t tgt) {
                 for (int32_t k0 = kb; k0 < ke; k0 += TILE128) {
                     const int32_t k1 = std::min(ke, k0 + TILE128);
                     if (col_level[rows[k0]] <= L + 1) emit_update_tiles(P.upd, p, k0, k1, nrow, tgt, TILE);
+                    else if (tgt == s && ozv >= 0 && col_level[rows[k0]] >= L + 3) continue;   // tcgen05 path (below)
                     else emit_update_tiles(P.upd128, p, k0, k1, nrow, tgt, TILE);
                 }
             };
@@ -208,6 +242,50 @@ void build_plan(const Symbolic& S, const PlanOptions& opt, Plan& P) {
         lp.ext_end = (int32_t)P.upd.size();
         lp.urgent_end = lp.ext_end;
         lp.lazy_end = (int32_t)P.upd128.size();
+
+        // tcgen05 tasks: piece j of an oz supernode completes the K range [0, 128 (j+1)) of column block c = j + 3
+        lp.oz_begin = (int32_t)P.oz_tasks.size();
+        lp.ozs_begin = (int32_t)P.oz_slices.size();
+        for (int32_t p : lpiece[L]) {
+            const Piece& pc = P.pieces[p];
+            const int32_t s = pc.sn;
+            const int32_t vi = P.sn_oz[s];
+            if (vi < 0) continue;
+            const OzViewPlan& v = P.oz_views[vi];
+            const int32_t f = S.sn_first[s], nc = sn_ncol(S, s), nrow = sn_nrow(S, s);
+            const int32_t j = (pc.c0 - f) / PIECE;
+            const int32_t c = j + 3;
+            if (c >= v.ncb) continue;
+            OzSlice sl;
+            sl.view = vi; sl.piece = p; sl.j = j; sl.pad = 0;
+            P.oz_slices.push_back(sl);
+            const int32_t nk32 = 4 * (j + 1);
+            const int32_t ncolc = std::min(128, nc - c * 128);
+            const int32_t nhalf = ncolc > 64 ? 2 : 1;
+            const int32_t nrbt = v.nrb - c;
+            const int32_t kmax = std::max(1, std::min(opt.oz_ksplit, 4096) / 32);
+            int32_t nsplit = (nk32 + kmax - 1) / kmax;
+            const int32_t want = (132 + nrbt * nhalf - 1) / (nrbt * nhalf);      // enough tasks for one wave ...
+            nsplit = std::max(nsplit, std::min(want, std::max(1, nk32 / 16)));  // ... but at least 512 columns each
+            const int32_t per = (nk32 + nsplit - 1) / nsplit;
+            for (int32_t k0 = 0; k0 < nk32; k0 += per)
+                for (int32_t a = c; a < v.nrb; ++a)
+                    for (int32_t h = 0; h < nhalf; ++h) {
+                        OzTask t;
+                        t.view = vi; t.rbA = a; t.rbB = c; t.half = h; t.k0 = k0; t.k1 = std::min(nk32, k0 + per);
+                        t.pad[0] = t.pad[1] = 0;
+                        P.oz_tasks.push_back(t);
+                        const int32_t ni = std::min(128, nrow - a * 128), nk = std::min(64, ncolc - h * 64);
+                        double ent = (double)ni * nk;
+                        if (a == c) {
+                            ent = 0.0;
+                            for (int32_t jj = h * 64; jj < h * 64 + nk; ++jj) ent += std::max(0, ni - jj);
+                        }
+                        P.flops_oz += 2.0 * ent * 32.0 * (t.k1 - t.k0);
+                    }
+        }
+        lp.oz_end = (int32_t)P.oz_tasks.size();
+        lp.ozs_end = (int32_t)P.oz_slices.size();
         lp.ext_atomic = 1;
 
         // Critical subset: the update tiles that land in a diagonal block of a next-level piece or anywhere in a

@@ -22,6 +22,8 @@ struct PlanOptions {
     int small_ncol = 32;      // nrow <= small_nrow run in the one-CTA kernels
     int small_nrow = 256;
     int big_ncol = 384;       // non-small supernodes with >= big_ncol columns use the dense-solve path (BigTask)
+    int oz_ncol = 1024;       // all-positive supernodes with >= oz_ncol columns: far Schur updates on the tcgen05 int8 path; <= 0 = off
+    int oz_ksplit = 2048;     // columns of K accumulated per tcgen05 task (multiple of 32, <= 4096: exact int32 accumulation)
 };
 
 // One column piece [c0,c1) of supernode sn (global permuted column indices), c1-c0 <= PIECE.
@@ -80,6 +82,30 @@ struct BigTask {
     int64_t tile0;    // first tile inside Ft / Bt
 };
 
+// ---- tcgen05 int8 (Ozaki) path of the far same-supernode updates (kernels_ozaki.cu) ---------------
+// Column block c of an "oz" supernode receives the contributions of its pieces 0 .. c-3 in ONE left-looking pass
+// (launched when piece c-3 is done, needed at level of piece c); pieces c-2 and c-1 stay on the FP64 DMMA path.
+// C[rbA*128 .. +128, rbB*128 + half*64 .. +64] -= L[rows A, 32*k0 .. 32*k1) * L[rows B, same]'   (lower part only)
+struct OzTask {
+    int32_t view;
+    int32_t rbA, rbB, half;
+    int32_t k0, k1;           // K-chunk range (32 columns each)
+    int32_t pad[2];
+};
+struct OzViewPlan {
+    int32_t sn;
+    int32_t nrb, ncb;         // 128-row blocks of the whole panel / 128-column blocks
+    int64_t off0;             // first entry of this view inside Plan::oz_rb_off
+    int64_t row0;             // first entry of this view's rows inside the E / scale arrays
+    int32_t base_level;       // level of the supernode's first piece (row scales are taken there)
+    int32_t pad;
+};
+struct OzSlice {
+    int32_t view, piece;      // piece id (Plan::pieces)
+    int32_t j;                // index of the piece inside its supernode
+    int32_t pad;
+};
+
 // backward sweep, rows below the columns of a tall supernode: p = L[rows, block]' x[rows] is accumulated into
 // DevCtx::bacc by a separate, fully parallel launch (k_bwd_below) before the level's block solves run
 struct BelowItem {
@@ -103,6 +129,8 @@ struct LevelPlan {
     int32_t fbig_begin = 0, fbig_end = 0;      // Plan::fwd_big (big supernodes that start at this level)
     int32_t bbig_begin = 0, bbig_end = 0;      // Plan::bwd_big
     int32_t below_begin = 0, below_end = 0;    // Plan::bwd_below
+    int32_t oz_begin = 0, oz_end = 0;          // Plan::oz_tasks launched when this level's pieces are done (needed at level + 3)
+    int32_t ozs_begin = 0, ozs_end = 0;        // Plan::oz_slices: pieces of this level whose digit planes are needed
     int32_t inv_end = 0;                       // Plan::inv_order[0, inv_end): diagonal blocks of pieces at levels <= this one
     int32_t pack_end = 0;                      // Plan::big_pack[0, pack_end): tiles whose column block is at a level <= this one
 };
@@ -133,6 +161,14 @@ struct Plan {
     std::vector<BelowItem> bwd_below;
     int64_t n_ftiles = 0, n_btiles = 0;   // tiles of Ft / Bt
     int32_t xq_slots = 0;                 // exchange slots (sum over big supernodes of ncb*128)
+    std::vector<int32_t> sn_oz;           // [nsuper] index into oz_views or -1
+    std::vector<OzViewPlan> oz_views;
+    std::vector<int64_t> oz_rb_off;       // per view nrb+1 entries: first K-chunk slot (32 KiB each) of every row block
+    int64_t oz_slots = 0;                 // total K-chunk slots of the digit planes
+    int64_t oz_rows = 0;                  // total panel rows of the oz views
+    std::vector<OzTask> oz_tasks;
+    std::vector<OzSlice> oz_slices;
+    double flops_oz = 0.0;                // algorithmic (lower-triangle) flops of the tcgen05 tasks
     std::vector<LevelPlan> levels;
     int32_t max_small_elems = 0;          // largest nrow*ncol among small supernodes
     int32_t max_small_nrow = 0;

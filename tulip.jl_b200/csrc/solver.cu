@@ -71,6 +71,19 @@ struct tlpb200_solver {
     int chain_sms_late = -1;      // same, from level chain_switch * nlevels on (TLPB200_CHAIN_SMS_LATE; -1 = same as chain_sms)
     double chain_switch = 0.5;    // TLPB200_CHAIN_SWITCH
 
+    // tcgen05 int8 (Ozaki) path of the far Schur updates inside big all-positive supernodes (kernels_ozaki.cu)
+    bool oz_on = false;
+    uint8_t* oz_planes = nullptr;
+    const int64_t* d_oz_rb_off = nullptr;
+    OzView* d_oz_views = nullptr;
+    const OzTask* d_oz_tasks = nullptr;
+    int32_t* oz_E = nullptr;
+    double* oz_scl = nullptr;
+    int32_t* oz_ctr = nullptr;                 // [2*nlevels] work-queue / exit counters
+    cudaStream_t oz_slice_stream = nullptr, oz_stream[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> ev_ozt, ev_ozs, ev_oz;   // per level: trsm done (main stream) / digit planes written / tasks done
+    int oz_sms_free = 16;                      // SMs the tcgen05 work queue leaves to the chain kernels (TLPB200_OZAKI_FREE_SMS)
+
     cudaGraphExec_t g_update = nullptr, g_solve = nullptr;
     bool profiling = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -79,8 +92,8 @@ struct tlpb200_solver {
     std::vector<cudaEvent_t> pool;
     std::vector<int> pool_cls;
     size_t pool_used = 0;
-    double ms_class[16] = {0};
-    int64_t n_class[16] = {0};
+    double ms_class[TLPB200_NCLASS] = {0};
+    int64_t n_class[TLPB200_NCLASS] = {0};
 
     int64_t launches_update = 0, launches_solve = 0;
     double ms_assemble = 0, ms_factor = 0, ms_solve = 0;
@@ -151,8 +164,8 @@ struct Scope {
 
 void collect_profile(tlpb200_solver* s, bool reset_update_classes) {
     // called after a stream sync
-    static const bool is_update_class[16] = {1, 1, 1, 1, 1, 0, 0, 0, 1, 0, 1, 0, 0, 1, 0, 0};   // class 12 (dense cols) is left cumulative
-    for (int c = 0; c < 16; ++c)
+    static const bool is_update_class[TLPB200_NCLASS] = {1, 1, 1, 1, 1, 0, 0, 0, 1, 0, 1, 0, 0, 1, 0, 0, 1, 1};   // class 12 (dense cols) is left cumulative
+    for (int c = 0; c < TLPB200_NCLASS; ++c)
         if (is_update_class[c] == reset_update_classes) { s->ms_class[c] = 0; s->n_class[c] = 0; }
     for (size_t i = 0; i + 1 < s->pool_used; i += 2) {
         float ms = 0;
@@ -186,6 +199,7 @@ void enqueue_assemble(tlpb200_solver* s, int64_t& count) {
         launch_compute_d(s->d_theta, s->d_regP, s->d_d, s->n, st);
         launch_assemble_k1(s->ctx, s->mat, s->d_d, s->d_regD, st);
         count += 3;
+        if (s->oz_on) CK(cudaMemsetAsync(s->oz_ctr, 0, (2 * s->plan.levels.size() + 2) * sizeof(int32_t), st));
     } else {
         launch_assemble_k2(s->ctx, s->mat, s->d_theta, s->d_regP, s->d_regD, st);
         count += 2;
@@ -221,6 +235,19 @@ void enqueue_factor(tlpb200_solver* s, int64_t& count) {
             s->ev_ur.push_back(c3[2]);
         }
     }
+    const bool oz = s->oz_on && s->cur == &s->ctx;
+    if (oz && overlap && s->ev_oz.size() < nlev) {
+        while (s->ev_oz.size() < nlev) {
+            cudaEvent_t e3[3];
+            for (auto& e : e3) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            s->ev_ozt.push_back(e3[0]);
+            s->ev_ozs.push_back(e3[1]);
+            s->ev_oz.push_back(e3[2]);
+        }
+    }
+    std::vector<char> has_oz(nlev, 0);
+    long oz_waited = -1;     // every tcgen05 batch of a level <= oz_waited has been joined by the main stream
+    int noz = 0;
     // columns that are final early are inverted / repacked for the solves underneath the tail of the factorisation
     const long pack_level = (overlap && s->pack_split > 0.0 && s->pack_split < 1.0 && !s->plan.big_pack.empty()) ? (long)(s->pack_split * (double)nlev) : -1;
     int32_t inv_done = 0, pack_done = 0;
@@ -235,6 +262,18 @@ void enqueue_factor(tlpb200_solver* s, int64_t& count) {
                 if (has_lazy[q]) CK(cudaStreamWaitEvent(st, s->ev_lazy[q], 0));
             waited = (long)l - 2;
         }
+        if (oz && overlap && l >= 3) {   // column block c of an oz supernode was completed by the batch of level c - 3
+            for (long q = oz_waited + 1; q <= (long)l - 3; ++q)
+                if (has_oz[q]) CK(cudaStreamWaitEvent(st, s->ev_oz[q], 0));
+            oz_waited = (long)l - 3;
+        }
+        if (oz)      // row scales of the oz supernodes that start at this level (before their first piece is factored)
+            for (const OzViewPlan& v : s->plan.oz_views)
+                if (v.base_level == (int32_t)l) {
+                    launch_oz_rowexp(s->ctx.Lx, s->ctx.diagpos, s->ctx.sn_rows + s->sym.sn_rowptr[v.sn],
+                                     (int32_t)(s->sym.sn_rowptr[v.sn + 1] - s->sym.sn_rowptr[v.sn]), s->oz_E + v.row0, s->oz_scl + v.row0, st);
+                    count++;
+                }
         if (lp.small_end > lp.small_begin) {
             Scope sc(s, 1);
             launch_small_factor((*s->cur), lp.small_begin, lp.small_end, s->small_smem, st);
@@ -274,6 +313,45 @@ void enqueue_factor(tlpb200_solver* s, int64_t& count) {
             }
             count++;
         }
+        if (oz && lp.ozs_end > lp.ozs_begin) {
+            // digit planes of this level's pieces (rows from column block j + 3 down), then the left-looking tcgen05 tasks
+            // of column block j + 3 over the pieces 0 .. j
+            cudaStream_t ss = st, us = st;
+            if (overlap) {
+                ss = s->oz_slice_stream;
+                us = s->oz_stream[noz++ & 1];
+                CK(cudaEventRecord(s->ev_ozt[l], st));
+                CK(cudaStreamWaitEvent(ss, s->ev_ozt[l], 0));
+                if (split) CK(cudaStreamWaitEvent(ss, s->ev_tr[l], 0));
+            }
+            {
+                Scope sc(s, 16);
+                for (int32_t x = lp.ozs_begin; x < lp.ozs_end; ++x) {
+                    const OzSlice& sl = s->plan.oz_slices[x];
+                    const OzViewPlan& v = s->plan.oz_views[sl.view];
+                    const Piece& pc = s->plan.pieces[sl.piece];
+                    const int32_t sn = v.sn;
+                    const int64_t ld = s->sym.sn_rowptr[sn + 1] - s->sym.sn_rowptr[sn];
+                    launch_oz_slice(s->ctx.Lx + s->sym.sn_xptr[sn], ld, (int32_t)ld, pc.c0 - s->sym.sn_first[sn], pc.c1 - pc.c0, sl.j + 3,
+                                    v.nrb - (sl.j + 3), 4 * sl.j, s->oz_E + v.row0, s->d_oz_rb_off + v.off0, s->oz_planes, ss);
+                    count++;
+                }
+            }
+            if (overlap) {
+                CK(cudaEventRecord(s->ev_ozs[l], ss));
+                CK(cudaStreamWaitEvent(us, s->ev_ozs[l], 0));
+            }
+            {
+                Scope sc(s, 17);
+                launch_oz_update(s->d_oz_views, s->d_oz_tasks, lp.oz_begin, lp.oz_end, s->oz_ctr + 2 * l, s->nsm, overlap ? s->oz_sms_free : 0,
+                                 s->ctx.info + 3, us);
+                count++;
+            }
+            if (overlap) {
+                CK(cudaEventRecord(s->ev_oz[l], us));
+                has_oz[l] = 1;
+            }
+        }
         if (pack_level >= 0 && (long)l >= pack_level && (lp.pack_end > pack_done || lp.inv_end > inv_done)) {
             // a slice of the invert / repack work per level: short-lived CTAs that fill idle SMs of the tail without
             // holding them against the chain kernels
@@ -302,6 +380,9 @@ void enqueue_factor(tlpb200_solver* s, int64_t& count) {
     if (overlap)
         for (long q = waited + 1; q < (long)nlev; ++q)
             if (has_lazy[q]) CK(cudaStreamWaitEvent(st, s->ev_lazy[q], 0));   // join
+    if (oz && overlap)
+        for (long q = oz_waited + 1; q < (long)nlev; ++q)
+            if (has_oz[q]) CK(cudaStreamWaitEvent(st, s->ev_oz[q], 0));   // join
     if (early_pack) CK(cudaStreamWaitEvent(st, s->ev_pack, 0));
     if ((*s->cur).ndblk > inv_done) { Scope sc(s, 10); launch_invert_diag((*s->cur), inv_done, (*s->cur).ndblk, st); count++; }
     if ((int32_t)s->plan.big_pack.size() > pack_done) { Scope sc(s, 13); launch_pack_big((*s->cur), pack_done, (int32_t)s->plan.big_pack.size(), st); count++; }
@@ -466,6 +547,8 @@ int finish_update(tlpb200_solver* s, int64_t* bad_pivot) {
     const int32_t info = *s->h_info;
     if (s->h_info[2] != 0)
         return fail(s, TLPB200_INTERNAL, "dense-solve hand-over timed out in an earlier solve (exchange slot never published)");
+    if (s->h_info[3] != 0)
+        return fail(s, TLPB200_INTERNAL, "tcgen05 update pipeline timed out (mbarrier never completed)");
     s->bad_pivot = (info >= 0 && info < s->sym.N) ? info : -1;
     if (bad_pivot) *bad_pivot = s->bad_pivot;
     if (s->bad_pivot >= 0) {
@@ -545,6 +628,7 @@ void setup_device(tlpb200_solver* s) {
     s->stream = s->own_stream;
     CK(kernels_static_init());
     CK(dense_solve_static_init());
+    CK(ozaki_static_init());
     for (auto& ev : s->ev) CK(cudaEventCreate(&ev));
 
     const Symbolic& S = s->sym;
@@ -624,6 +708,34 @@ void setup_device(tlpb200_solver* s) {
         s->ctxA = s->ctx; s->ctxA.skip = upload(s, skipA);
         s->ctxB = s->ctx; s->ctxB.skip = upload(s, skipB);
         s->d_keep = const_cast<int8_t*>(upload(s, keep));
+    }
+    if (!P.oz_views.empty()) {
+        int lo = 0, hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CK(cudaStreamCreateWithPriority(&s->oz_slice_stream, cudaStreamNonBlocking, std::min(lo, hi + 1)));
+        for (auto& x : s->oz_stream) CK(cudaStreamCreateWithPriority(&x, cudaStreamNonBlocking, lo));
+        s->oz_planes = dalloc<uint8_t>(s, (size_t)P.oz_slots * OZ_S * 4096);
+        CK(cudaMemset(s->oz_planes, 0, (size_t)P.oz_slots * OZ_S * 4096));
+        s->d_oz_rb_off = upload(s, P.oz_rb_off);
+        s->d_oz_tasks = upload(s, P.oz_tasks);
+        s->oz_E = dalloc<int32_t>(s, (size_t)P.oz_rows);
+        s->oz_scl = dalloc<double>(s, (size_t)P.oz_rows);
+        s->oz_ctr = dalloc<int32_t>(s, 2 * P.levels.size() + 2);
+        std::vector<OzView> hv(P.oz_views.size());
+        for (size_t i = 0; i < hv.size(); ++i) {
+            const OzViewPlan& v = P.oz_views[i];
+            OzView& o = hv[i];
+            o.planes = s->oz_planes;
+            o.rb_off = s->d_oz_rb_off + v.off0;
+            o.C = c.Lx + S.sn_xptr[v.sn];
+            o.ldc = S.sn_rowptr[v.sn + 1] - S.sn_rowptr[v.sn];
+            o.scl = s->oz_scl + v.row0;
+            o.nrows = (int32_t)o.ldc;
+            o.ncols = S.sn_first[v.sn + 1] - S.sn_first[v.sn];
+        }
+        s->d_oz_views = const_cast<OzView*>(upload(s, hv));
+        s->oz_on = true;
+        if (const char* e = getenv("TLPB200_OZAKI_FREE_SMS")) s->oz_sms_free = std::max(0, std::min(prop.multiProcessorCount - 1, atoi(e)));
     }
     s->nsm = prop.multiProcessorCount;
     if (const char* e = getenv("TLPB200_CHAIN_SMS")) s->chain_sms = std::max(0, std::min(s->nsm - 1, atoi(e)));
@@ -781,6 +893,10 @@ int tlpb200_create(tlpb200_solver** out, int64_t m, int64_t n, const int64_t* co
         po.small_elems = s->opt.small_elems;
         if (s->opt.dense_solve_ncol > 0) po.big_ncol = s->opt.dense_solve_ncol;
         if (const char* e = getenv("TLPB200_DENSE_SOLVE_NCOL")) po.big_ncol = std::max(1, atoi(e));
+        // tcgen05 int8 path: single-GPU K1 only (the K2 panels carry negative pivots; sharded runs keep the FP64 path)
+        po.oz_ncol = (system == TLPB200_K1 && s->nranks == 1) ? (s->opt.ozaki_ncol != 0 ? s->opt.ozaki_ncol : po.oz_ncol) : -1;
+        if (const char* e = getenv("TLPB200_OZAKI_NCOL")) { if (po.oz_ncol > 0 || atoi(e) <= 0) po.oz_ncol = atoi(e); }
+        if (const char* e = getenv("TLPB200_OZAKI_KSPLIT")) po.oz_ksplit = std::max(32, (atoi(e) / 32) * 32);
         build_plan(s->sym, po, s->plan);
         if (system == TLPB200_K1)
             build_assembly_k1(s->sym, m, n, cp_f, ri_f, va_f, s->maps);
@@ -955,7 +1071,10 @@ int tlpb200_stats_get(const tlpb200_solver* s, tlpb200_stats* o) {
     o->bytes_device = (int64_t)s->bytes_device;
     o->flops_update_inner = s->plan.flops_panel;
     o->flops_update_ext = s->plan.flops_update;
-    for (int c = 0; c < 16; ++c) { o->ms_class[c] = s->ms_class[c]; o->n_class[c] = s->n_class[c]; }
+    for (int c = 0; c < TLPB200_NCLASS; ++c) { o->ms_class[c] = s->ms_class[c]; o->n_class[c] = s->n_class[c]; }
+    o->flops_update_oz = s->plan.flops_oz;
+    o->oz_tasks = (int64_t)s->plan.oz_tasks.size();
+    o->oz_bytes = s->plan.oz_slots * (int64_t)(OZ_S * 4096);
     return TLPB200_OK;
 }
 
