@@ -262,12 +262,38 @@ def gpu_arm(args):
         except Exception:
             traffic = None
     ach = flops_upd / (ms_upd * 1e-3) / 1e12 if ms_upd > 0 else 0.0
-    roofline = {"kernel": "k_update (FP64 DMMA m8n8k4 tile update: supernode SYRK/GEMM + scatter)",
-                "bound": "tensor", "achieved": round(ach, 3), "peak": round(dgemm_tf, 2), "unit": "TFLOP/s",
-                "frac": round(ach / dgemm_tf, 4) if dgemm_tf > 0 else None, "traffic": traffic,
-                "peak_source": "cuBLAS DGEMM 4096^3 measured live in this run (MEASURED_PEAKS.json has no FP64 figure; nominal B200 FP64 = 40 TFLOP/s)",
-                "launches_per_step": int(n_upd), "avg_launch_ms": round(ms_upd / max(1, n_upd), 4),
-                "algorithmic_flops_per_step": flops_upd, "share_of_update_ms": round(ms_upd / max(1e-9, sp["ms_assemble"] + sp["ms_factor"]), 3)}
+    roofline_dmma = {"kernel": "k_update (FP64 DMMA m8n8k4 tile update: supernode SYRK/GEMM + scatter)",
+                     "bound": "tensor", "achieved": round(ach, 3), "peak": round(dgemm_tf, 2), "unit": "TFLOP/s",
+                     "frac": round(ach / dgemm_tf, 4) if dgemm_tf > 0 else None, "traffic": traffic,
+                     "peak_source": "cuBLAS DGEMM 4096^3 measured live in this run (MEASURED_PEAKS.json has no FP64 figure; nominal B200 FP64 = 40 TFLOP/s)",
+                     "launches_per_step": int(n_upd), "avg_launch_ms": round(ms_upd / max(1, n_upd), 4),
+                     "algorithmic_flops_per_step": flops_upd, "share_of_update_ms": round(ms_upd / max(1e-9, sp["ms_assemble"] + sp["ms_factor"]), 3)}
+    ms_oz, n_oz = cls["oz_update"]
+    if n_oz > 0 and sp["flops_update_oz"] > 0:
+        # dominant kernel: the tcgen05 int8 (Ozaki) update.  One FP64 multiply-add = 36 int8 digit-plane multiply-adds, so
+        # the algorithmic tensor work is 36 x the FP64 flops; peak = dense int8 rate = 2 x the measured dense bf16 rate
+        # (B200: 4.5 vs 2.25 POP/s nominal), burst figure because profiling mode times every launch alone.
+        int8_peak = 2.0 * float(peaks.get("bf16_tflops", 1590.0))
+        tops = 36.0 * sp["flops_update_oz"] / (ms_oz * 1e-3) / 1e12
+        tp2 = os.path.join(ROOT, "profiles", "k_oz_update_traffic.json")
+        traffic_oz = None
+        if os.path.exists(tp2):
+            try:
+                traffic_oz = json.load(open(tp2)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic_oz = None
+        roofline = {"kernel": "k_oz_update (tcgen05.mma kind::i8, 36 digit-plane products per FP64 product, accumulators in TMEM)",
+                    "bound": "tensor", "achieved": round(tops, 1), "peak": round(int8_peak, 1), "unit": "TOP/s (int8)",
+                    "frac": round(tops / int8_peak, 4), "traffic": traffic_oz,
+                    "peak_source": f"2 x dense bf16 {peak_src} (no int8 figure in MEASURED_PEAKS.json; int8 dense = 2 x bf16 dense on B200)",
+                    "fp64_equivalent_tflops": round(sp["flops_update_oz"] / (ms_oz * 1e-3) / 1e12, 2),
+                    "fp64_dgemm_tflops_measured": round(dgemm_tf, 2),
+                    "launches_per_step": int(n_oz), "avg_launch_ms": round(ms_oz / n_oz, 4),
+                    "algorithmic_flops_per_step": sp["flops_update_oz"], "tasks_per_step": sp["oz_tasks"],
+                    "share_of_update_ms": round(ms_oz / max(1e-9, sp["ms_assemble"] + sp["ms_factor"]), 3),
+                    "note": "CUDA-event bracket around every launch of the class, kernels serialised (profiling mode)"}
+    else:
+        roofline = roofline_dmma
     ms_tri = sum(cls[k][0] for k in ("fwd_small", "fwd_large", "bwd_large", "bwd_small", "fwd_big", "bwd_big"))
     # dominant solve kernels: the dense sweeps over the big supernodes (k_fwd_big + k_bwd_big); their algorithmic
     # bytes are 16 B per non-zero of the big supernodes' panels (L read once forward, once backward: SURVEY 8d)
@@ -308,7 +334,7 @@ def gpu_arm(args):
         "gpu_launches": launches,
         "update_ms_host_api": round(float(np.mean([r["t_update"] for r in timed])) * 1e3, 3),
         "solve_ms_host_api": round(float(np.sum([r["t_solve"] for r in timed]) / np.sum([len(r["rhs"]) for r in timed])) * 1e3, 3),
-        "roofline": roofline, "roofline_solve": roofline_solve, "phases_one_step": phases,
+        "roofline": roofline, "roofline_dmma": roofline_dmma, "roofline_solve": roofline_solve, "phases_one_step": phases,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_sample(pkg, lp, sysname, recs[W])

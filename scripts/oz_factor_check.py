@@ -6,7 +6,11 @@ import tlpb200_loader; pkg = tlpb200_loader.load()
 from tulip_jl_b200 import lpgen
 from oracle import kkt_ref
 cfg = sys.argv[1] if len(sys.argv) > 1 else "2"
-lp = lpgen.config(int(cfg) if cfg.isdigit() else cfg); A = lp.A; m, n = A.shape
+if cfg == "M":
+    lp = lpgen.random_sparse(30000, 60000, 7, seed=777, name="mid_random_3e4")
+else:
+    lp = lpgen.config(int(cfg) if cfg.isdigit() else cfg)
+A = lp.A; m, n = A.shape
 rng = np.random.default_rng(0)
 th = np.exp(rng.uniform(-5, 5, n)); rP = np.full(n, 1e-6); rD = np.full(m, 1e-6)
 xp = rng.standard_normal(m); xd = rng.standard_normal(n)
@@ -15,12 +19,12 @@ for name, nc in (("fp64", -1), ("ozaki", 0)):
     k = pkg.setup(A, pkg.K1(), pkg.Backend(ozaki_ncol=nc))
     dx = np.zeros(n); dy = np.zeros(m)
     ts = []
-    for _ in range(6):
+    for _ in range(int(os.environ.get('NUPD', '6'))):
         t0 = time.perf_counter(); k.update(th, rP, rD); ts.append(time.perf_counter() - t0)
     k.solve(dx, dy, xp, xd)
     rp, rd = kkt_ref.kkt_residuals(A, th, rP, rD, dx, dy, xp, xd)
     st = k.stats()
-    print(f"{name}: update ms {[round(t * 1e3, 2) for t in ts]} residuals {rp:.2e} {rd:.2e} oz_tasks={st['oz_tasks']} "
+    print(f"{name}: nnzL={st['nnzL']:.3e} flops={st['flops']:.3e} nsuper={st['nsuper']} levels={st['nlevels']} update ms {[round(t * 1e3, 2) for t in ts]} residuals {rp:.2e} {rd:.2e} oz_tasks={st['oz_tasks']} "
           f"oz GB={st['oz_bytes'] / 1e9:.2f} launches={st['launches_update']}", flush=True)
     lx[name] = k.debug_lx()[0]
     if name == "ozaki":

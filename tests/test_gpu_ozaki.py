@@ -28,7 +28,7 @@ def _ozaki(P, C0, ksplit):
     return Cf
 
 
-@pytest.mark.parametrize("R,K,ksplit,spread", [(128, 32, 0, 0.0), (300, 200, 64, 0.0), (640, 1024, 256, 8.0), (513, 2048, 0, 3.0)])
+@pytest.mark.parametrize("R,K,ksplit,spread", [(128, 32, 0, 0.0), (300, 200, 64, 0.0), (260, 1024, 256, 8.0), (200, 2048, 0, 3.0)])
 def test_digit_plane_products_are_fp64_grade(R, K, ksplit, spread):
     """C -= P P' through int8 digit planes == the 80-bit product rounded once per RED, up to the dropped digit pairs
     (~2^-57 of the row scales sqrt(K_ii K_jj): below FP64 rounding of an ordinary GEMM)."""

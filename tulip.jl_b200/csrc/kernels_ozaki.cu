@@ -67,7 +67,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 }
 // bounded wait: a broken pipeline raises err[0] instead of hanging the device
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int32_t* err) {
-    for (int spin = 0; spin < (1 << 24); ++spin) {
+    for (int spin = 0; spin < (1 << 20); ++spin) {
         uint32_t ok;
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -173,21 +173,12 @@ __global__ void __launch_bounds__(128) k_oz_slice(const double* __restrict__ pan
 // tile update
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(OZ_THREADS, 1) k_oz_update(const OzView* __restrict__ views, const OzTask* __restrict__ tasks, int32_t begin,
-                                                             int32_t end, int32_t* counter, int32_t first_reserved_sm, int32_t* err) {
+                                                             int32_t end, int32_t* counter, int32_t* err) {
     extern __shared__ uint8_t oz_smem_raw[];
     __shared__ OzShared sh;
     const uint32_t raw = smem_u32(oz_smem_raw);
     const uint32_t stage0 = (raw + 1023u) & ~1023u;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-    unsigned smid;
-    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    if ((int32_t)smid >= first_reserved_sm) {       // leave the reserved SMs to the critical chain, but never all of them
-        if (tid == 0) sh.next = atomicAdd(counter + 1, 1);
-        __syncthreads();
-        if (sh.next + 1 < (int32_t)gridDim.x) return;
-        __syncthreads();
-    }
 
     if (tid == 0) {
         for (int s = 0; s < OZ_NSTAGE; ++s) {
@@ -212,7 +203,10 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) k_oz_update(const OzView* __res
     uint32_t ntask = 0;       // tasks processed so far by this CTA
     bool alive = true;
     for (;;) {
-        if (tid == 0) sh.next = begin + atomicAdd(counter, 1);
+        if (tid == 0) {
+            const int32_t nx = begin + atomicAdd(counter, 1);
+            sh.next = (*reinterpret_cast<volatile int32_t*>(err) != 0) ? end : nx;     // a timed-out pipeline drains the queue at once
+        }
         __syncthreads();
         const int32_t task = sh.next;
         if (task >= end) break;
@@ -322,8 +316,11 @@ void launch_oz_slice(const double* panel, int64_t ld, int32_t nrows, int32_t c0,
 void launch_oz_update(const OzView* views, const OzTask* tasks, int32_t begin, int32_t end, int32_t* counter, int nsm, int reserve,
                       int32_t* err, cudaStream_t st) {
     if (end <= begin) return;
-    const int grid = std::min(end - begin + reserve, nsm);
-    k_oz_update<<<grid, OZ_THREADS, OZ_SMEM, st>>>(views, tasks, begin, end, counter, nsm - reserve, err);
+    // One CTA owns a whole SM (192 KiB of shared memory, all of TMEM).  SMs are kept free for the critical-chain kernels by
+    // the grid size, not by SM id: a CTA that exits because of where it landed is replaced by the next pending CTA of the
+    // same grid on the same SM, and when the other SMs are busy the whole grid drains through the reserved ones.
+    const int grid = std::min(end - begin, std::max(1, nsm - reserve));
+    k_oz_update<<<grid, OZ_THREADS, OZ_SMEM, st>>>(views, tasks, begin, end, counter, err);
 }
 
 }  // namespace tlp

@@ -319,7 +319,8 @@ void enqueue_factor(tlpb200_solver* s, int64_t& count) {
             cudaStream_t ss = st, us = st;
             if (overlap) {
                 ss = s->oz_slice_stream;
-                us = s->oz_stream[noz++ & 1];
+                us = s->oz_stream[0];   // one stream: at most nsm - oz_sms_free tcgen05 CTAs are ever resident
+                noz++;
                 CK(cudaEventRecord(s->ev_ozt[l], st));
                 CK(cudaStreamWaitEvent(ss, s->ev_ozt[l], 0));
                 if (split) CK(cudaStreamWaitEvent(ss, s->ev_tr[l], 0));
