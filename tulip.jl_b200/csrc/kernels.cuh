@@ -164,7 +164,7 @@ void launch_oz_rowexp(const double* Lx, const int64_t* diagpos, const int32_t* g
 void launch_oz_slice(const double* panel, int64_t ld, int32_t nrows, int32_t c0, int32_t w, int32_t rb0, int32_t nrb, int32_t kchunk0,
                      const int32_t* E, const int64_t* rb_off, uint8_t* planes, cudaStream_t st);
 void launch_oz_update(const OzView* views, const OzTask* tasks, int32_t begin, int32_t end, int32_t* counter, int nsm, int reserve,
-                      int32_t* err, cudaStream_t st);
+                      int32_t* err, int tile_n, cudaStream_t st);   // tile_n: 64 (one pass, 128x64 tiles) | 128 (two passes, 128x128)
 
 size_t small_factor_smem(int32_t max_elems, int32_t max_nrow);
 cudaError_t kernels_static_init();   // cudaFuncSetAttribute calls

@@ -22,6 +22,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "../../include/tlpb200.h"
@@ -86,12 +87,12 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                  "r"(bytes), "r"(bar)
                  : "memory");
 }
-__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate, uint32_t idesc = OZ_IDESC) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}\n" ::"r"(tmem_d),
-        "l"(da), "l"(db), "r"(OZ_IDESC), "r"(accumulate), "r"(0u)
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u)
         : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -299,8 +300,166 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) k_oz_update(const OzView* __res
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// 128 x 128 tile, two passes over K (TLPB200_OZAKI_TILE=128).  The 128 x 64 kernel above re-reads 6 KiB of shared memory
+// per 32-cycle MMA (192 B/clk against the 128 B/clk the SM delivers), so the tensor pipe idles a third of the time.  With
+// N = 128 an MMA reads 8 KiB per 64 cycles (128 B/clk); the 8 accumulators of a tile then need 1024 TMEM columns, so the
+// levels are done in two passes that each own all 512 columns: pass 0 = levels 0..3 (10 plane pairs, planes 0..3 only),
+// pass 1 = levels 4..7 (26 pairs).  Each pass drains into registers (16 epilogue warps x 32 columns), hands TMEM back and
+// issues its REDs underneath the next pass's MMAs.
+// ------------------------------------------------------------------------------------------
+constexpr int OZ2_THREADS = 576;                  // producer warp, MMA warp, 16 epilogue warps (4 per TMEM lane quarter)
+constexpr int OZ2_STAGE = 2 * OZ_STAGE_A;          // 64 KiB: A planes at 0, B planes at 32 KiB
+constexpr int OZ2_NSTAGE = 3;
+constexpr size_t OZ2_SMEM = (size_t)OZ2_NSTAGE * OZ2_STAGE + 1024;
+constexpr uint32_t OZ2_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+__global__ void __launch_bounds__(OZ2_THREADS, 1) k_oz_update2(const OzView* __restrict__ views, const OzTask* __restrict__ tasks, int32_t begin,
+                                                               int32_t end, int32_t* counter, int32_t* err) {
+    extern __shared__ uint8_t oz_smem_raw[];
+    __shared__ OzShared sh;
+    const uint32_t raw = smem_u32(oz_smem_raw);
+    const uint32_t stage0 = (raw + 1023u) & ~1023u;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        for (int s = 0; s < OZ2_NSTAGE; ++s) {
+            mbar_init(smem_u32(&sh.full[s]), 1);
+            mbar_init(smem_u32(&sh.empty[s]), 1);
+        }
+        mbar_init(smem_u32(&sh.acc_full), 1);
+        mbar_init(smem_u32(&sh.acc_empty), 16);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&sh.tmem_base)), "n"(OZ_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t tmem = sh.tmem_base;
+
+    uint32_t it = 0;          // stages produced / consumed so far
+    uint32_t npass = 0;       // passes done so far by this CTA (2 per task)
+    bool alive = true;
+    for (;;) {
+        if (tid == 0) {
+            const int32_t nx = begin + atomicAdd(counter, 1);
+            sh.next = (*reinterpret_cast<volatile int32_t*>(err) != 0) ? end : nx;
+        }
+        __syncthreads();
+        const int32_t task = sh.next;
+        if (task >= end) break;
+        const OzTask T = tasks[task];
+        const OzView V = views[T.view];
+        const int32_t nk = T.k1 - T.k0;
+
+        if (tid == 0) {
+            // ===== producer: pass 0 streams planes 0..3 of both operands, pass 1 all 8 =====
+            const uint8_t* a = V.planes + (V.rb_off[T.rbA] + (int64_t)T.k0) * (int64_t)OZ_STAGE_A;
+            const uint8_t* b = V.planes + (V.rb_off[T.rbB] + (int64_t)T.k0) * (int64_t)OZ_STAGE_A;
+            uint32_t i = it;
+            for (int pass = 0; pass < 2; ++pass) {
+                const uint32_t bytes = pass == 0 ? OZ_STAGE_A / 2 : OZ_STAGE_A;
+                for (int32_t kc = 0; kc < nk && alive; ++kc, ++i) {
+                    const uint32_t s = i % OZ2_NSTAGE, ph = (i / OZ2_NSTAGE) & 1u;
+                    alive = mbar_wait(smem_u32(&sh.empty[s]), ph ^ 1u, err);
+                    const uint32_t fb = smem_u32(&sh.full[s]);
+                    const uint32_t dst = stage0 + s * OZ2_STAGE;
+                    mbar_expect_tx(fb, 2 * bytes);
+                    bulk_g2s(dst, a + (int64_t)kc * OZ_STAGE_A, bytes, fb);
+                    bulk_g2s(dst + OZ_STAGE_A, b + (int64_t)kc * OZ_STAGE_A, bytes, fb);
+                }
+            }
+        } else if (tid == 32) {
+            // ===== MMA issuer =====
+            uint32_t i = it;
+            for (int pass = 0; pass < 2; ++pass) {
+                const uint32_t np = npass + pass;
+                alive = alive && mbar_wait(smem_u32(&sh.acc_empty), (np & 1u) ^ 1u, err);
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                for (int32_t kc = 0; kc < nk && alive; ++kc, ++i) {
+                    const uint32_t s = i % OZ2_NSTAGE, ph = (i / OZ2_NSTAGE) & 1u;
+                    alive = mbar_wait(smem_u32(&sh.full[s]), ph, err);
+                    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                    const uint32_t sa = stage0 + s * OZ2_STAGE, sb = sa + OZ_STAGE_A;
+                    if (pass == 0) {
+#pragma unroll
+                        for (int p = 0; p < 4; ++p)
+#pragma unroll
+                            for (int q = 0; q + p < 4; ++q)
+                                umma_i8(tmem + (uint32_t)((p + q) * 128), oz_desc(sa + p * OZ_BLK), oz_desc(sb + q * OZ_BLK),
+                                        (kc > 0 || p > 0) ? 1u : 0u, OZ2_IDESC);
+                    } else {
+#pragma unroll
+                        for (int p = 0; p < OZ_S; ++p)
+#pragma unroll
+                            for (int q = 0; q + p < OZ_S; ++q)
+                                if (p + q >= 4)
+                                    umma_i8(tmem + (uint32_t)((p + q - 4) * 128), oz_desc(sa + p * OZ_BLK), oz_desc(sb + q * OZ_BLK),
+                                            (kc > 0 || p > 0) ? 1u : 0u, OZ2_IDESC);
+                    }
+                    umma_commit(smem_u32(&sh.empty[s]));
+                }
+                umma_commit(smem_u32(&sh.acc_full));
+            }
+        } else if (warp >= 2) {
+            // ===== epilogue: 16 warps; TMEM lane quarter = warp % 4, column quarter = (warp - 2) / 4; thread = output row =====
+            const int q4 = warp & 3, ch = (warp - 2) >> 2;
+            const int32_t gi = T.rbA * 128 + q4 * 32 + lane;
+            const int32_t gj0 = T.rbB * 128 + ch * 32;
+            const bool rv = gi < V.nrows;
+            const double sr = rv ? V.scl[gi] : 0.0;
+            double* crow = V.C + gi;
+            const uint32_t tbase = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(ch * 32);
+            for (int pass = 0; pass < 2; ++pass) {
+                alive = alive && mbar_wait(smem_u32(&sh.acc_full), (npass + pass) & 1u, err);
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                double val[32];
+#pragma unroll
+                for (int cc = 0; cc < 32; cc += 8) {
+                    int32_t a[4][8];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) tmem_ld8(tbase + (uint32_t)(t * 128 + cc), a[t]);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        long long v = a[0][e];
+#pragma unroll
+                        for (int t = 1; t < 4; ++t) v = v * 256 + a[t][e];
+                        val[cc + e] = (double)v;
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&sh.acc_empty));      // TMEM is free: the next pass starts underneath the REDs
+                if (rv) {
+                    const double si = sr * (pass == 0 ? 0x1p-36 : 0x1p-68);
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        const int32_t gj = gj0 + e;
+                        if (gj < V.ncols && gi >= gj) atomicAdd(crow + (int64_t)gj * V.ldc, -(val[e] * si * V.scl[gj]));
+                    }
+                }
+            }
+        }
+        it += 2u * (uint32_t)nk;
+        npass += 2u;
+        __syncthreads();
+    }
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(OZ_TMEM_COLS) : "memory");
+    }
+}
+
 cudaError_t ozaki_static_init() {
-    return cudaFuncSetAttribute(k_oz_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(k_oz_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_oz_update2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ2_SMEM);
 }
 
 void launch_oz_rowexp(const double* Lx, const int64_t* diagpos, const int32_t* grow, int32_t nrows, int32_t* E, double* scl,
@@ -314,13 +473,14 @@ void launch_oz_slice(const double* panel, int64_t ld, int32_t nrows, int32_t c0,
 }
 
 void launch_oz_update(const OzView* views, const OzTask* tasks, int32_t begin, int32_t end, int32_t* counter, int nsm, int reserve,
-                      int32_t* err, cudaStream_t st) {
+                      int32_t* err, int tile_n, cudaStream_t st) {
     if (end <= begin) return;
     // One CTA owns a whole SM (192 KiB of shared memory, all of TMEM).  SMs are kept free for the critical-chain kernels by
     // the grid size, not by SM id: a CTA that exits because of where it landed is replaced by the next pending CTA of the
     // same grid on the same SM, and when the other SMs are busy the whole grid drains through the reserved ones.
     const int grid = std::min(end - begin, std::max(1, nsm - reserve));
-    k_oz_update<<<grid, OZ_THREADS, OZ_SMEM, st>>>(views, tasks, begin, end, counter, err);
+    if (tile_n == 128) k_oz_update2<<<grid, OZ2_THREADS, OZ2_SMEM, st>>>(views, tasks, begin, end, counter, err);
+    else k_oz_update<<<grid, OZ_THREADS, OZ_SMEM, st>>>(views, tasks, begin, end, counter, err);
 }
 
 }  // namespace tlp
@@ -355,10 +515,11 @@ extern "C" int tlpb200_debug_ozaki(const double* P, int64_t R, int64_t K, double
         E[r] = (e + 1) >> 1;
         scl[r] = ldexp(1.0, E[r]);
     }
+    const int tile_n = (getenv("TLPB200_OZAKI_TILE") && atoi(getenv("TLPB200_OZAKI_TILE")) == 128) ? 128 : 64;
     std::vector<OzTask> tasks;
     for (int32_t b = 0; b < nrb; ++b)
         for (int32_t a = b; a < nrb; ++a)
-            for (int32_t h = 0; h < 2; ++h)
+            for (int32_t h = 0; h < (tile_n == 128 ? 1 : 2); ++h)
                 for (int32_t k0 = 0; k0 < nk32; k0 += kstep) {
                     OzTask t{};
                     t.view = 0; t.rbA = a; t.rbB = b; t.half = h; t.k0 = k0; t.k1 = std::min(nk32, k0 + kstep);
@@ -403,7 +564,7 @@ extern "C" int tlpb200_debug_ozaki(const double* P, int64_t R, int64_t K, double
         launch_oz_slice(dP, R, (int32_t)R, j * 128, (int32_t)std::min<int64_t>(128, K - (int64_t)j * 128), 0, nrb, 4 * j, dE, doff, dpl, 0);
     OZCK(cudaEventRecord(e1));
     OZCK(cudaMemset(dctr, 0, 8));
-    launch_oz_update(dview, dtask, 0, (int32_t)tasks.size(), dctr, nsm, 0, derr, 0);
+    launch_oz_update(dview, dtask, 0, (int32_t)tasks.size(), dctr, nsm, 0, derr, tile_n, 0);
     OZCK(cudaDeviceSynchronize());
     OZCK(cudaEventElapsedTime(&ms[0], e0, e1));
     OZCK(cudaMemcpy(C, dC, (size_t)R * R * 8, cudaMemcpyDeviceToHost));
@@ -413,7 +574,7 @@ extern "C" int tlpb200_debug_ozaki(const double* P, int64_t R, int64_t K, double
         OZCK(cudaEventRecord(e0));
         for (int r = 0; r < reps; ++r) {
             OZCK(cudaMemsetAsync(dctr, 0, 8, 0));
-            launch_oz_update(dview, dtask, 0, (int32_t)tasks.size(), dctr, nsm, 0, derr, 0);
+            launch_oz_update(dview, dtask, 0, (int32_t)tasks.size(), dctr, nsm, 0, derr, tile_n, 0);
         }
         OZCK(cudaEventRecord(e1));
         OZCK(cudaDeviceSynchronize());

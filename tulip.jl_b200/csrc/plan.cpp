@@ -246,6 +246,20 @@ void build_plan(const Symbolic& S, const PlanOptions& opt, Plan& P) {
         // tcgen05 tasks: piece j of an oz supernode completes the K range [0, 128 (j+1)) of column block c = j + 3
         lp.oz_begin = (int32_t)P.oz_tasks.size();
         lp.ozs_begin = (int32_t)P.oz_slices.size();
+        {
+            int64_t n128 = 0;     // 128x128 tasks this level's launch would have
+            const int32_t kmax0 = std::max(1, std::min(opt.oz_ksplit, 4096) / 32);
+            for (int32_t p : lpiece[L]) {
+                const Piece& pc = P.pieces[p];
+                const int32_t vi = P.sn_oz[pc.sn];
+                if (vi < 0) continue;
+                const OzViewPlan& v = P.oz_views[vi];
+                const int32_t j = (pc.c0 - S.sn_first[pc.sn]) / PIECE;
+                if (j + 3 >= v.ncb) continue;
+                n128 += (int64_t)(v.nrb - (j + 3)) * ((4 * (j + 1) + kmax0 - 1) / kmax0);
+            }
+            lp.oz_tile = opt.oz_tile_n == 128 ? 128 : (opt.oz_tile_n == 64 ? 64 : (n128 >= 264 ? 128 : 64));
+        }
         for (int32_t p : lpiece[L]) {
             const Piece& pc = P.pieces[p];
             const int32_t s = pc.sn;
@@ -261,7 +275,8 @@ void build_plan(const Symbolic& S, const PlanOptions& opt, Plan& P) {
             P.oz_slices.push_back(sl);
             const int32_t nk32 = 4 * (j + 1);
             const int32_t ncolc = std::min(128, nc - c * 128);
-            const int32_t nhalf = ncolc > 64 ? 2 : 1;
+            const int32_t nhalf = (lp.oz_tile == 128) ? 1 : (ncolc > 64 ? 2 : 1);
+            const int32_t tn = lp.oz_tile;
             const int32_t nrbt = v.nrb - c;
             const int32_t kmax = std::max(1, std::min(opt.oz_ksplit, 4096) / 32);
             int32_t nsplit = (nk32 + kmax - 1) / kmax;
@@ -275,7 +290,7 @@ void build_plan(const Symbolic& S, const PlanOptions& opt, Plan& P) {
                         t.view = vi; t.rbA = a; t.rbB = c; t.half = h; t.k0 = k0; t.k1 = std::min(nk32, k0 + per);
                         t.pad[0] = t.pad[1] = 0;
                         P.oz_tasks.push_back(t);
-                        const int32_t ni = std::min(128, nrow - a * 128), nk = std::min(64, ncolc - h * 64);
+                        const int32_t ni = std::min(128, nrow - a * 128), nk = std::min(tn, ncolc - h * 64);
                         double ent = (double)ni * nk;
                         if (a == c) {
                             ent = 0.0;

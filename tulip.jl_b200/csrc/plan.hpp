@@ -23,6 +23,9 @@ struct PlanOptions {
     int small_nrow = 256;
     int big_ncol = 384;       // non-small supernodes with >= big_ncol columns use the dense-solve path (BigTask)
     int oz_ncol = 1024;       // all-positive supernodes with >= oz_ncol columns: far Schur updates on the tcgen05 int8 path; <= 0 = off
+    int oz_tile_n = 0;        // 64: 128x64 tiles, one pass | 128: 128x128 tiles, two passes over K (k_oz_update2) | 0: per level,
+                              // 128 when the launch has at least two waves of 128x128 tasks (measured: 68 vs 57 TF on large
+                              // launches, but coarser tasks lose on small ones)
     int oz_ksplit = 2048;     // columns of K accumulated per tcgen05 task (multiple of 32, <= 4096: exact int32 accumulation)
 };
 
@@ -131,6 +134,7 @@ struct LevelPlan {
     int32_t below_begin = 0, below_end = 0;    // Plan::bwd_below
     int32_t oz_begin = 0, oz_end = 0;          // Plan::oz_tasks launched when this level's pieces are done (needed at level + 3)
     int32_t ozs_begin = 0, ozs_end = 0;        // Plan::oz_slices: pieces of this level whose digit planes are needed
+    int32_t oz_tile = 64;                      // output tile width of this level's tcgen05 launch (64 | 128)
     int32_t inv_end = 0;                       // Plan::inv_order[0, inv_end): diagonal blocks of pieces at levels <= this one
     int32_t pack_end = 0;                      // Plan::big_pack[0, pack_end): tiles whose column block is at a level <= this one
 };

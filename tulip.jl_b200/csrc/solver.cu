@@ -345,7 +345,7 @@ void enqueue_factor(tlpb200_solver* s, int64_t& count) {
             {
                 Scope sc(s, 17);
                 launch_oz_update(s->d_oz_views, s->d_oz_tasks, lp.oz_begin, lp.oz_end, s->oz_ctr + 2 * l, s->nsm, overlap ? s->oz_sms_free : 0,
-                                 s->ctx.info + 3, us);
+                                 s->ctx.info + 3, lp.oz_tile, us);
                 count++;
             }
             if (overlap) {
@@ -897,6 +897,7 @@ int tlpb200_create(tlpb200_solver** out, int64_t m, int64_t n, const int64_t* co
         // tcgen05 int8 path: single-GPU K1 only (the K2 panels carry negative pivots; sharded runs keep the FP64 path)
         po.oz_ncol = (system == TLPB200_K1 && s->nranks == 1) ? (s->opt.ozaki_ncol != 0 ? s->opt.ozaki_ncol : po.oz_ncol) : -1;
         if (const char* e = getenv("TLPB200_OZAKI_NCOL")) { if (po.oz_ncol > 0 || atoi(e) <= 0) po.oz_ncol = atoi(e); }
+        if (const char* e = getenv("TLPB200_OZAKI_TILE")) po.oz_tile_n = atoi(e) == 128 ? 128 : (atoi(e) == 64 ? 64 : 0);
         if (const char* e = getenv("TLPB200_OZAKI_KSPLIT")) po.oz_ksplit = std::max(32, (atoi(e) / 32) * 32);
         build_plan(s->sym, po, s->plan);
         if (system == TLPB200_K1)
