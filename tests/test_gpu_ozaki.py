@@ -98,3 +98,24 @@ def test_profiled_update_uses_the_tensor_path():
     cls = dict(zip(pkg._lib.KERNEL_CLASSES, st["n_class"]))
     assert cls["oz_update"] > 0 and cls["oz_slice"] > 0
     assert st["flops_update_oz"] > st["flops_update_ext"] * 0.2
+
+
+def test_breakdown_with_the_tensor_path_raises_and_recovers():
+    """spd.jl:47 / step.jl:34-51: a factorisation breakdown inside a supernode that uses the tcgen05 path must surface as
+    PosDefException (never a hang or a pipeline time-out), and the retry with larger regularisations must succeed."""
+    lp = _medium_lp()
+    A = lp.A
+    m, n = A.shape
+    rng = np.random.default_rng(5)
+    k = pkg.setup(A, pkg.K1(), pkg.Backend(ozaki_ncol=512))
+    theta = np.exp(rng.uniform(-2, 2, n)); regP = np.full(n, 1e-6)
+    with pytest.raises(pkg.PosDefException):
+        k.update(theta, regP, np.full(m, -1e6))            # K = A D A' - 1e6 I is indefinite
+    regD = np.full(m, 1e-6)
+    k.update(theta, regP, regD)
+    xp = rng.standard_normal(m); xd = rng.standard_normal(n)
+    dx = np.zeros(n); dy = np.zeros(m)
+    k.solve(dx, dy, xp, xd)
+    rp, rd = kkt_ref.kkt_residuals(A, theta, regP, regD, dx, dy, xp, xd)
+    scale = max(1.0, np.abs(dx).max(), np.abs(dy).max())
+    assert rp <= 1e-9 * scale and rd <= 1e-9 * scale
