@@ -23,7 +23,7 @@ const libtlpb200 = get(ENV, "TLPB200_LIB", joinpath(@__DIR__, "..", "libtlpb200.
 const OK, NOT_POSDEF, OOM, BAD_ARG, CUDA_ERR, INTERNAL = 0, 1, 2, 3, 4, 5
 
 """
-    Backend(; device=0, ordering=1, piece_width=128, small_elems=4096, use_graph=true)
+    Backend(; device=0, ordering=1, piece_width=128, small_elems=4096, use_graph=true, ozaki_ncol=0, ...)
 
 B200 (sm_100a) supernodal direct solver for the K1 / K2 systems.  Options are fields of the tag,
 like `TlpKrylov.Backend` (src/KKT/Krylov/krylov.jl:41-44).
@@ -35,6 +35,10 @@ Base.@kwdef struct Backend <: AbstractKKTBackend
     small_elems::Int32 = 4096
     relax_always::Int32 = 8
     use_graph::Bool = true
+    dense_col_threshold::Int32 = 0   # K1 dense-column Schur path: 0 auto, < 0 off
+    dense_solve_ncol::Int32 = 0      # supernodes with >= this many columns use the dense-solve sweeps (0 = 384)
+    ozaki_ncol::Int32 = 0            # K1: supernodes with >= this many columns run their far Schur updates on the
+                                     # tcgen05 int8 tensor-core path (0 = 1024, < 0 = FP64 DMMA path everywhere)
 end
 
 # layout must match `tlpb200_options`
@@ -42,7 +46,8 @@ struct COptions
     ordering::Int32; device::Int32; piece_width::Int32; small_elems::Int32
     relax_always::Int32; use_graph::Int32; analyze_only::Int32
     rank::Int32; nranks::Int32; dense_col_threshold::Int32
-    reserved::NTuple{6,Int32}
+    dense_solve_ncol::Int32; ozaki_ncol::Int32
+    reserved::NTuple{4,Int32}
 end
 
 mutable struct B200Solver{S<:AbstractKKTSystem} <: AbstractKKTSolver{Float64}
@@ -54,7 +59,8 @@ mutable struct B200Solver{S<:AbstractKKTSystem} <: AbstractKKTSolver{Float64}
     function B200Solver{S}(A::SparseMatrixCSC{Float64,Int}, sys::Int, b::Backend) where {S}
         m, n = size(A)
         opt = Ref(COptions(b.ordering, b.device, b.piece_width, b.small_elems, b.relax_always,
-                           b.use_graph ? 1 : 0, 0, 0, 1, 0, ntuple(_ -> Int32(0), 6)))
+                           b.use_graph ? 1 : 0, 0, 0, 1, b.dense_col_threshold, b.dense_solve_ncol, b.ozaki_ncol,
+                           ntuple(_ -> Int32(0), 4)))
         h = Ref{Ptr{Cvoid}}(C_NULL)
         rc = ccall((:tlpb200_create, libtlpb200), Cint,
                    (Ref{Ptr{Cvoid}}, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Cint, Cint, Ref{COptions}),
