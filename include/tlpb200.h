@@ -147,6 +147,11 @@ int tlpb200_debug_factor_trace(tlpb200_solver* s, uint64_t* out, int64_t* nlevel
  * -= P P' with P R x K column-major; `ksplit` = K columns per task (multiple of 32, 0 = all).  ms[0] = digit-plane
  * kernels, ms[1] = one update pass (mean of `reps`), ms[2] = tasks; *err != 0 = pipeline time-out. */
 int tlpb200_debug_ozaki(const double* P, int64_t R, int64_t K, double* C, int32_t ksplit, int32_t reps, float* ms, int32_t* err);
+/* Update-task plan as int32 records (host data, also on analyze_only handles): upd / upd128 = FP64 tile tasks
+ * {piece, i0, ni, k0, nk, tgt, diag, pad}, oz = tcgen05 tasks {view, rbA, rbB, half, k0, k1, pad, pad}, pieces =
+ * {sn, c0, c1, level}, views = {sn, nrb, ncb, base_level}; counts[5] = their lengths.  NULL arrays are skipped. */
+int tlpb200_debug_update_plan(const tlpb200_solver* s, int64_t* counts, int32_t* upd, int32_t* upd128, int32_t* oz, int32_t* pieces,
+                              int32_t* views);
 int tlpb200_debug_big_plan(const tlpb200_solver* s, int64_t* counts, void* pack, void* fwd, void* bwd);
 
 /* ---- multi-GPU, one process per GPU (no counterpart in the reference, NEWS.md:31) -------------

@@ -1174,6 +1174,35 @@ int tlpb200_debug_big_plan(const tlpb200_solver* s, int64_t* counts, void* pack,
     return TLPB200_OK;
 }
 
+// update-task plan (host data; tests/test_update_plan.py checks that the FP64 tiles and the tcgen05 tasks cover every
+// (piece, target entry) pair exactly once).  Arrays are int32 records: upd / upd128 = UpdTask (8), oz = OzTask (8),
+// pieces = Piece (4), views = {sn, nrb, ncb, base_level}.
+int tlpb200_debug_update_plan(const tlpb200_solver* s, int64_t* counts, int32_t* upd, int32_t* upd128, int32_t* oz, int32_t* pieces,
+                              int32_t* views) {
+    if (!s) return TLPB200_BAD_ARG;
+    const Plan& P = s->plan;
+    static_assert(sizeof(UpdTask) == 32 && sizeof(OzTask) == 32 && sizeof(Piece) == 16, "record sizes");
+    if (counts) {
+        counts[0] = (int64_t)P.upd.size();
+        counts[1] = (int64_t)P.upd128.size();
+        counts[2] = (int64_t)P.oz_tasks.size();
+        counts[3] = (int64_t)P.pieces.size();
+        counts[4] = (int64_t)P.oz_views.size();
+    }
+    if (upd && !P.upd.empty()) std::memcpy(upd, P.upd.data(), P.upd.size() * sizeof(UpdTask));
+    if (upd128 && !P.upd128.empty()) std::memcpy(upd128, P.upd128.data(), P.upd128.size() * sizeof(UpdTask));
+    if (oz && !P.oz_tasks.empty()) std::memcpy(oz, P.oz_tasks.data(), P.oz_tasks.size() * sizeof(OzTask));
+    if (pieces && !P.pieces.empty()) std::memcpy(pieces, P.pieces.data(), P.pieces.size() * sizeof(Piece));
+    if (views)
+        for (size_t i = 0; i < P.oz_views.size(); ++i) {
+            views[4 * i + 0] = P.oz_views[i].sn;
+            views[4 * i + 1] = P.oz_views[i].nrb;
+            views[4 * i + 2] = P.oz_views[i].ncb;
+            views[4 * i + 3] = P.oz_views[i].base_level;
+        }
+    return TLPB200_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Multi-GPU (one process per GPU): subtree-sharded factorisation.  The caller (tulip.jl_b200/parallel.py,
 // torch.distributed / NCCL) performs the collectives between the phases on the exposed device buffers.

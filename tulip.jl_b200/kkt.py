@@ -301,6 +301,18 @@ class B200KKTSolver:
             _raise(rc, self._h)
         return out.astype(np.int64)
 
+    def update_plan(self):
+        """Update-task plan (host data, available on analyze_only handles): FP64 tile tasks, tcgen05 tasks, pieces, views."""
+        lib = _lib.load()
+        cnt = np.zeros(5, np.int64)
+        lib.tlpb200_debug_update_plan(self._h, cnt.ctypes.data_as(C.POINTER(C.c_int64)), None, None, None, None, None)
+        upd = np.zeros((int(cnt[0]), 8), np.int32); upd128 = np.zeros((int(cnt[1]), 8), np.int32)
+        oz = np.zeros((int(cnt[2]), 8), np.int32); pieces = np.zeros((int(cnt[3]), 4), np.int32)
+        views = np.zeros((int(cnt[4]), 4), np.int32)
+        vp = lambda a: C.c_void_p(a.ctypes.data)
+        lib.tlpb200_debug_update_plan(self._h, cnt.ctypes.data_as(C.POINTER(C.c_int64)), vp(upd), vp(upd128), vp(oz), vp(pieces), vp(views))
+        return {"upd": upd, "upd128": upd128, "oz": oz, "pieces": pieces, "views": views}
+
     def big_plan(self):
         """Dense-solve plan of the big supernodes (host data, available on analyze_only handles)."""
         lib = _lib.load()
