@@ -1390,6 +1390,11 @@ void tlpb200_destroy(tlpb200_solver* s) {
         for (auto& ev : s->ev_d) cudaEventDestroy(ev);
         for (auto& ev : s->ev_tr) cudaEventDestroy(ev);
         for (auto& ev : s->ev_ur) cudaEventDestroy(ev);
+        for (auto& ev : s->ev_ozt) cudaEventDestroy(ev);
+        for (auto& ev : s->ev_ozs) cudaEventDestroy(ev);
+        for (auto& ev : s->ev_oz) cudaEventDestroy(ev);
+        if (s->oz_slice_stream) cudaStreamDestroy(s->oz_slice_stream);
+        for (auto& x : s->oz_stream) if (x) cudaStreamDestroy(x);
         if (s->own_stream) cudaStreamDestroy(s->own_stream);
     }
     delete s;
