@@ -9,8 +9,6 @@
 //
 // FP64 on B200: DMMA.8x8x4 and DFMA both peak at 64 FMA/clk/SM (measured 37.1 TFLOP/s,
 // scripts/dmma_bench.cu); every mma.sync f64 shape lowers to DMMA.8x8x4.  tcgen05 has no FP64 kind.
-#include <cstdlib>
-
 #include "kernels.cuh"
 
 namespace tlp {
@@ -208,151 +206,6 @@ __global__ void __launch_bounds__(DF_THREADS, 1) k_diag_factor(DevCtx c, int32_t
     __syncthreads();
     for (int k = q4; k < w; k += 4)
         if (il < w && il >= k) D[(int64_t)k * ld + il] = (il == k) ? dd[k] : Cs[k * LDD + il] * rdd[k];
-    if (tid == 0) trace_mark(c, pc.level, 0, true);
-}
-
-// ------------------------------------------------------------------------------------------
-// k_diag_factor32: the same signed Cholesky of a w x w (<= 128) diagonal block, blocked by 32 columns
-// (opt-in with TLPB200_DIAG32=1; measured slower than k_diag_factor above on B200, see launch_diag_factor):
-//   (1) warp 0 factors the 32 x 32 diagonal sub-block in registers (lane = row, shuffles broadcast the
-//       pivot column; one rsqrt per column),
-//   (2) one thread per row below solves its 32 entries by substitution (row in registers),
-//   (3) all 16 warps apply the rank-32 update to the trailing lower triangle (warp = rows mod 16,
-//       lane = columns mod 32: conflict-free column reads, broadcast row reads).
-// 4 sub-blocks x 3 barriers instead of 16 x 4: the block sits on the critical chain of every level.
-// ------------------------------------------------------------------------------------------
-constexpr int NB32 = 32;
-constexpr int LDL32 = NB32 + 1;
-
-__global__ void __launch_bounds__(DF_THREADS, 1) k_diag_factor32(DevCtx c, int32_t begin) {
-    extern __shared__ double smem_d[];
-    double* Cs = smem_d;                   // [PIECE][LDD] column-major
-    double* Ld = Cs + PIECE * LDD;         // [NB32][LDL32]  Ld[m][j] = l_mj of the current diagonal sub-block
-    double* sgn = Ld + NB32 * LDL32;       // [PIECE]
-    double* inv = sgn + PIECE;             // [NB32] 1 / (s_j l_jj)
-    const Piece pc = c.pieces[c.level_pieces[begin + blockIdx.x]];
-    const int32_t s = pc.sn;
-    if (c.skip && c.skip[s]) return;
-    const int32_t f = c.sn_first[s];
-    const int32_t ld = (int32_t)(c.sn_rowptr[s + 1] - c.sn_rowptr[s]);
-    const int32_t lc0 = pc.c0 - f, w = pc.c1 - pc.c0;
-    double* D = c.Lx + c.sn_xptr[s] + (int64_t)lc0 * ld + lc0;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int il = tid & (PIECE - 1), q4 = tid >> 7;
-
-    if (tid == 0) trace_mark(c, pc.level, 0, false);
-    if (tid < PIECE) sgn[tid] = (tid < w) ? (double)c.sign[pc.c0 + tid] : 1.0;
-    for (int kb = 0; kb < w; kb += 32) {       // 8 independent loads in flight per thread
-        double v[8];
-#pragma unroll
-        for (int x = 0; x < 8; ++x) {
-            const int k = kb + q4 + 4 * x;
-            v[x] = (k < w && il < w && il >= k) ? D[(int64_t)k * ld + il] : 0.0;
-        }
-#pragma unroll
-        for (int x = 0; x < 8; ++x) {
-            const int k = kb + q4 + 4 * x;
-            if (k < w) Cs[k * LDD + il] = v[x];
-        }
-    }
-    __syncthreads();
-
-    for (int j0 = 0; j0 < w; j0 += NB32) {
-        const int nb = min(NB32, w - j0), r0 = j0 + nb;
-        // (1) diagonal sub-block, warp 0
-        if (warp == 0) {
-            double a[NB32];
-#pragma unroll
-            for (int k = 0; k < NB32; ++k) a[k] = (lane < nb && k <= lane) ? Cs[(j0 + k) * LDD + j0 + lane] : 0.0;
-#pragma unroll
-            for (int j = 0; j < NB32; ++j) {
-                double d = __shfl_sync(0xffffffffu, a[j], j);
-                if (j < nb) {                                       // uniform
-                    const double sj = sgn[j0 + j];
-                    if (!(d * sj > 0.0)) {
-                        if (lane == 0) atomicMin(c.info, pc.c0 + j0 + j);
-                        d = sj;
-                    }
-                    const double rs = rsqrt(d * sj);
-                    const double ljj = d * sj * rs;
-                    const double iv = sj * rs;                      // 1 / (s_j l_jj)
-                    const double lij = (lane > j) ? a[j] * iv : (lane == j ? ljj : 0.0);
-                    a[j] = lij;
-                    if (lane == j) inv[j] = iv;
-                    const double t = lij * sj;
-#pragma unroll
-                    for (int m = j + 1; m < NB32; ++m) {
-                        const double lmj = __shfl_sync(0xffffffffu, lij, m);
-                        a[m] -= t * lmj;                            // only lanes >= m keep a meaningful a[m]
-                    }
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < NB32; ++k)
-                if (lane < nb && k <= lane) {
-                    Cs[(j0 + k) * LDD + j0 + lane] = a[k];
-                    Ld[lane * LDL32 + k] = a[k];
-                }
-        }
-        __syncthreads();
-        if (r0 >= w) break;
-        // (2) rows below: x_j = (a_j - sum_{k<j} x_k s_k l_jk) / (s_j l_jj), one row per thread
-        if (tid < w - r0) {
-            const int i = r0 + tid;
-            double x[NB32];
-#pragma unroll
-            for (int k = 0; k < NB32; ++k) x[k] = (k < nb) ? Cs[(j0 + k) * LDD + i] : 0.0;
-#pragma unroll
-            for (int j = 0; j < NB32; ++j)
-                if (j < nb) {
-                    const double xj = x[j] * inv[j];
-                    x[j] = xj;
-                    const double t = xj * sgn[j0 + j];
-#pragma unroll
-                    for (int m = j + 1; m < NB32; ++m)
-                        if (m < nb) x[m] -= t * Ld[m * LDL32 + j];
-                }
-#pragma unroll
-            for (int k = 0; k < NB32; ++k)
-                if (k < nb) Cs[(j0 + k) * LDD + i] = x[k];
-        }
-        __syncthreads();
-        // (3) trailing update: C[i][m] -= sum_k x_ik s_k x_mk for i >= m >= r0; row i = r0 + warp + 16 ii, column m = r0 + lane + 32 mm
-        {
-            const int r = w - r0;
-            double acc[6][3];
-#pragma unroll
-            for (int ii = 0; ii < 6; ++ii)
-#pragma unroll
-                for (int mm = 0; mm < 3; ++mm) acc[ii][mm] = 0.0;
-            for (int k = 0; k < nb; ++k) {
-                const double* col = Cs + (j0 + k) * LDD + r0;
-                const double sk = sgn[j0 + k];
-                double av[6], bv[3];
-#pragma unroll
-                for (int ii = 0; ii < 6; ++ii) av[ii] = (warp + 16 * ii < r) ? col[warp + 16 * ii] : 0.0;
-#pragma unroll
-                for (int mm = 0; mm < 3; ++mm) bv[mm] = (lane + 32 * mm < r) ? col[lane + 32 * mm] * sk : 0.0;
-#pragma unroll
-                for (int ii = 0; ii < 6; ++ii)
-#pragma unroll
-                    for (int mm = 0; mm < 3; ++mm)
-                        if (16 * ii + 15 >= 32 * mm) acc[ii][mm] += av[ii] * bv[mm];      // compile-time: skip all-upper blocks
-            }
-#pragma unroll
-            for (int ii = 0; ii < 6; ++ii)
-#pragma unroll
-                for (int mm = 0; mm < 3; ++mm)
-                    if (16 * ii + 15 >= 32 * mm) {
-                        const int i = warp + 16 * ii, m = lane + 32 * mm;
-                        if (i < r && m <= i) Cs[(r0 + m) * LDD + r0 + i] -= acc[ii][mm];
-                    }
-        }
-        __syncthreads();
-    }
-    __syncthreads();
-    for (int k = q4; k < w; k += 4)
-        if (il < w && il >= k) D[(int64_t)k * ld + il] = Cs[k * LDD + il];
     if (tid == 0) trace_mark(c, pc.level, 0, true);
 }
 
@@ -611,14 +464,11 @@ __global__ void __launch_bounds__(UPD_THREADS, 4) k_update_lazy(DevCtx c, int32_
 // launchers
 // ------------------------------------------------------------------------------------------
 static constexpr size_t DF_SMEM = ((size_t)PIECE * LDD + 3 * PIECE + (size_t)NBD * LDW + (size_t)PIECE * LDW) * 8;
-static constexpr size_t DF32_SMEM = ((size_t)PIECE * LDD + (size_t)NB32 * LDL32 + PIECE + NB32) * 8;
 static constexpr size_t TR_SMEM = ((size_t)PIECE * LDX + (size_t)PIECE * LDLB + (size_t)TRB * LDX + (size_t)TRB * LDLD + TRB) * 8;
 
 cudaError_t factor_kernels_static_init() {
     cudaError_t e;
     e = cudaFuncSetAttribute(k_diag_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DF_SMEM);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_diag_factor32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DF32_SMEM);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TR_SMEM);
     if (e != cudaSuccess) return e;
@@ -629,12 +479,7 @@ cudaError_t factor_kernels_static_init() {
 }
 
 void launch_diag_factor(const DevCtx& c, int32_t begin, int32_t end, cudaStream_t st) {
-    // measured on cfg2 (B200): the 32-column blocked variant is slower on the chain (update! 15.8 ms vs 12.2 ms) -- the
-    // in-register 32 x 32 warp factorisation costs more than it saves in barriers -- so it stays opt-in
-    static const bool blocked32 = getenv("TLPB200_DIAG32") && atoi(getenv("TLPB200_DIAG32")) != 0;
-    if (end <= begin) return;
-    if (blocked32) k_diag_factor32<<<end - begin, DF_THREADS, DF32_SMEM, st>>>(c, begin);
-    else k_diag_factor<<<end - begin, DF_THREADS, DF_SMEM, st>>>(c, begin);
+    if (end > begin) k_diag_factor<<<end - begin, DF_THREADS, DF_SMEM, st>>>(c, begin);
 }
 void launch_trsm(const DevCtx& c, int32_t begin, int32_t end, cudaStream_t st) {
     if (end > begin) k_trsm<<<end - begin, TR_THREADS, TR_SMEM, st>>>(c, begin);
