@@ -9,8 +9,9 @@
 //         x 2^-E = d_0 2^-6 + sum_{p>=1} d_p 2^(-6-8p),   d_0 in [-64, 64], d_p in [-128, 127]     (k_oz_slice, exact, 63 bits)
 //     stored as int8 planes in the layout the tensor core reads (K-major, no swizzle, 8x16-byte core matrices).
 //   * product of digit planes p, q has weight 2^(-12-8(p+q)); all pairs with p+q = t <= 7 accumulate EXACTLY (int32,
-//     |acc| <= 8 K 2^14: K <= 4096 per task) into TMEM accumulator t.  The dropped pairs (p+q >= 8) are ~2^-57 of the row
-//     scales -- far inside the classical Cholesky backward-error bound and below the FP64 rounding of the DMMA path.
+//     |acc| <= 8 K 2^14: K <= 4096 per task) into TMEM accumulator t.  The dropped pairs (p+q >= 8) are the whole error:
+//     ~2^-50 sqrt(K/4096) of sqrt(K_ii K_jj) -- the size of an FP64 GEMM's rounding error on the same data, far inside the
+//     classical Cholesky backward-error bound (tests/test_ozaki_math.py is the NumPy specification).
 //   * epilogue: the 8 accumulators of an output entry are combined in int64, converted once, scaled by 2^(E_i+E_j-68)
 //     and subtracted from the target panel with RED.ADD.F64.
 //

@@ -79,8 +79,8 @@ struct tlpb200_solver {
     const OzTask* d_oz_tasks = nullptr;
     int32_t* oz_E = nullptr;
     double* oz_scl = nullptr;
-    int32_t* oz_ctr = nullptr;                 // [2*nlevels] work-queue / exit counters
-    cudaStream_t oz_slice_stream = nullptr, oz_stream[2] = {nullptr, nullptr};
+    int32_t* oz_ctr = nullptr;                 // [2*nlevels] work-queue counters of the tcgen05 launches
+    cudaStream_t oz_slice_stream = nullptr, oz_stream = nullptr;
     std::vector<cudaEvent_t> ev_ozt, ev_ozs, ev_oz;   // per level: trsm done (main stream) / digit planes written / tasks done
     int oz_sms_free = 16;                      // SMs the tcgen05 work queue leaves to the chain kernels (TLPB200_OZAKI_FREE_SMS)
 
@@ -247,7 +247,6 @@ void enqueue_factor(tlpb200_solver* s, int64_t& count) {
     }
     std::vector<char> has_oz(nlev, 0);
     long oz_waited = -1;     // every tcgen05 batch of a level <= oz_waited has been joined by the main stream
-    int noz = 0;
     // columns that are final early are inverted / repacked for the solves underneath the tail of the factorisation
     const long pack_level = (overlap && s->pack_split > 0.0 && s->pack_split < 1.0 && !s->plan.big_pack.empty()) ? (long)(s->pack_split * (double)nlev) : -1;
     int32_t inv_done = 0, pack_done = 0;
@@ -319,8 +318,7 @@ void enqueue_factor(tlpb200_solver* s, int64_t& count) {
             cudaStream_t ss = st, us = st;
             if (overlap) {
                 ss = s->oz_slice_stream;
-                us = s->oz_stream[0];   // one stream: at most nsm - oz_sms_free tcgen05 CTAs are ever resident
-                noz++;
+                us = s->oz_stream;      // one stream: at most nsm - oz_sms_free tcgen05 CTAs are ever resident
                 CK(cudaEventRecord(s->ev_ozt[l], st));
                 CK(cudaStreamWaitEvent(ss, s->ev_ozt[l], 0));
                 if (split) CK(cudaStreamWaitEvent(ss, s->ev_tr[l], 0));
@@ -714,7 +712,7 @@ void setup_device(tlpb200_solver* s) {
         int lo = 0, hi = 0;
         CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         CK(cudaStreamCreateWithPriority(&s->oz_slice_stream, cudaStreamNonBlocking, std::min(lo, hi + 1)));
-        for (auto& x : s->oz_stream) CK(cudaStreamCreateWithPriority(&x, cudaStreamNonBlocking, lo));
+        CK(cudaStreamCreateWithPriority(&s->oz_stream, cudaStreamNonBlocking, lo));
         s->oz_planes = dalloc<uint8_t>(s, (size_t)P.oz_slots * OZ_S * 4096);
         CK(cudaMemset(s->oz_planes, 0, (size_t)P.oz_slots * OZ_S * 4096));
         s->d_oz_rb_off = upload(s, P.oz_rb_off);
@@ -1394,7 +1392,7 @@ void tlpb200_destroy(tlpb200_solver* s) {
         for (auto& ev : s->ev_ozs) cudaEventDestroy(ev);
         for (auto& ev : s->ev_oz) cudaEventDestroy(ev);
         if (s->oz_slice_stream) cudaStreamDestroy(s->oz_slice_stream);
-        for (auto& x : s->oz_stream) if (x) cudaStreamDestroy(x);
+        if (s->oz_stream) cudaStreamDestroy(s->oz_stream);
         if (s->own_stream) cudaStreamDestroy(s->own_stream);
     }
     delete s;
