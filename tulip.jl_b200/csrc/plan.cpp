@@ -316,15 +316,21 @@ void build_plan(const Symbolic& S, const PlanOptions& opt, Plan& P) {
                 const int32_t s = P.pieces[T.piece].sn;
                 const int32_t* rows = S.sn_rows.data() + S.sn_rowptr[s];
                 bool cr = false;
+                int32_t last_pf = -1;                 // piece already tested (and missed) by an earlier column of the tile
                 for (int32_t k = T.k0; k < T.k0 + T.nk && !cr; ++k) {
                     const int32_t gk = rows[k];
                     if (col_level[gk] != L + 1) continue;
                     const int32_t ts = S.col2sn[gk];
                     if (P.sn_small[ts]) { cr = true; break; }
                     const int32_t pf = S.sn_first[ts] + ((gk - S.sn_first[ts]) / PIECE) * PIECE;
+                    if (pf == last_pf) continue;
+                    last_pf = pf;
                     const int32_t pl = std::min(pf + PIECE, S.sn_first[ts + 1]);
-                    for (int32_t i = T.i0; i < T.i0 + T.ni; ++i)
-                        if (rows[i] >= pf && rows[i] < pl) { cr = true; break; }
+                    // the row list is ascending: does the tile's row range meet [pf, pl)?
+                    const int32_t* rb = rows + T.i0;
+                    const int32_t* re = rb + T.ni;
+                    const int32_t* it = std::lower_bound(rb, re, pf);
+                    if (it != re && *it < pl) cr = true;
                 }
                 if (!cr) continue;
                 ucrit[x - lp.ext_begin] = 1;

@@ -843,7 +843,17 @@ int tlpb200_create(tlpb200_solver** out, int64_t m, int64_t n, const int64_t* co
     s->m = m;
     s->n = n;
     try {
+        static const bool trace_setup = getenv("TLPB200_TRACE") != nullptr;
+        auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        double t_mark = now();
+        auto lap = [&](const char* what) {
+            if (!trace_setup) return;
+            const double t = now();
+            fprintf(stderr, "tlpb200 setup: %-22s %8.3f s\n", what, t - t_mark);
+            t_mark = t;
+        };
         canonicalize(s, colptr, rowval, nzval, index_base);
+        lap("canonicalize");
         SymOptions so;
         so.ordering = s->opt.ordering;
         if (s->opt.relax_always > 0) so.relax_always = s->opt.relax_always;
@@ -876,6 +886,7 @@ int tlpb200_create(tlpb200_solver** out, int64_t m, int64_t n, const int64_t* co
         }
         if (system == TLPB200_K1) {
             SymPattern P = pattern_k1(m, n, cp_f, ri_f);
+            lap("pattern");
             analyze_pattern(P, so, nullptr, s->sym);
         } else {
             SymPattern P = pattern_k2(m, n, s->colptr.data(), s->rowidx.data());
@@ -883,6 +894,7 @@ int tlpb200_create(tlpb200_solver** out, int64_t m, int64_t n, const int64_t* co
             for (int64_t j = 0; j < n; ++j) sg[j] = -1;   // first n pivots < 0, last m > 0 (systems.jl:10-32)
             analyze_pattern(P, so, sg.data(), s->sym);
         }
+        lap("analyze_pattern");
         s->rank = s->opt.rank;
         s->nranks = std::max(1, s->opt.nranks);
         if (s->rank < 0 || s->rank >= s->nranks) throw std::invalid_argument("rank out of range");
@@ -898,11 +910,14 @@ int tlpb200_create(tlpb200_solver** out, int64_t m, int64_t n, const int64_t* co
         if (const char* e = getenv("TLPB200_OZAKI_TILE")) po.oz_tile_n = atoi(e) == 128 ? 128 : (atoi(e) == 64 ? 64 : 0);
         if (const char* e = getenv("TLPB200_OZAKI_KSPLIT")) po.oz_ksplit = std::max(32, (atoi(e) / 32) * 32);
         build_plan(s->sym, po, s->plan);
+        lap("build_plan");
         if (system == TLPB200_K1)
             build_assembly_k1(s->sym, m, n, cp_f, ri_f, va_f, s->maps);
         else
             build_assembly_k2(s->sym, m, n, s->colptr.data(), s->rowidx.data(), s->maps);
+        lap("assembly maps");
         if (!s->opt.analyze_only) setup_device(s);
+        lap("setup_device");
     } catch (const CudaFail& f) {
         return cuda_fail(s, f);
     } catch (const std::bad_alloc&) {
@@ -1176,17 +1191,23 @@ int tlpb200_debug_big_plan(const tlpb200_solver* s, int64_t* counts, void* pack,
 // (piece, target entry) pair exactly once).  Arrays are int32 records: upd / upd128 = UpdTask (8), oz = OzTask (8),
 // pieces = Piece (4), views = {sn, nrb, ncb, base_level}.
 int tlpb200_debug_update_plan(const tlpb200_solver* s, int64_t* counts, int32_t* upd, int32_t* upd128, int32_t* oz, int32_t* pieces,
-                              int32_t* views) {
+                              int32_t* views, int32_t* panel, int32_t* levels) {
     if (!s) return TLPB200_BAD_ARG;
     const Plan& P = s->plan;
-    static_assert(sizeof(UpdTask) == 32 && sizeof(OzTask) == 32 && sizeof(Piece) == 16, "record sizes");
+    static_assert(sizeof(UpdTask) == 32 && sizeof(OzTask) == 32 && sizeof(Piece) == 16 && sizeof(PanelTask) == 16, "record sizes");
+    static_assert(sizeof(LevelPlan) % sizeof(int32_t) == 0, "LevelPlan is a record of int32");
     if (counts) {
         counts[0] = (int64_t)P.upd.size();
         counts[1] = (int64_t)P.upd128.size();
         counts[2] = (int64_t)P.oz_tasks.size();
         counts[3] = (int64_t)P.pieces.size();
         counts[4] = (int64_t)P.oz_views.size();
+        counts[5] = (int64_t)P.panel.size();
+        counts[6] = (int64_t)P.levels.size();
+        counts[7] = (int64_t)(sizeof(LevelPlan) / sizeof(int32_t));
     }
+    if (panel && !P.panel.empty()) std::memcpy(panel, P.panel.data(), P.panel.size() * sizeof(PanelTask));
+    if (levels && !P.levels.empty()) std::memcpy(levels, P.levels.data(), P.levels.size() * sizeof(LevelPlan));
     if (upd && !P.upd.empty()) std::memcpy(upd, P.upd.data(), P.upd.size() * sizeof(UpdTask));
     if (upd128 && !P.upd128.empty()) std::memcpy(upd128, P.upd128.data(), P.upd128.size() * sizeof(UpdTask));
     if (oz && !P.oz_tasks.empty()) std::memcpy(oz, P.oz_tasks.data(), P.oz_tasks.size() * sizeof(OzTask));

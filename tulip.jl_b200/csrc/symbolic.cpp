@@ -7,6 +7,9 @@
 
 #include <algorithm>
 #include <cassert>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <numeric>
 #include <stdexcept>
 
@@ -204,6 +207,15 @@ std::vector<int32_t> column_counts(const SymPattern& P, const std::vector<int32_
 void analyze_pattern(const SymPattern& P0, const SymOptions& opt, const int8_t* orig_sign, Symbolic& S) {
     const int32_t N = P0.N;
     S.N = N;
+    static const bool trace = getenv("TLPB200_TRACE") != nullptr;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_mark = now();
+    auto lap = [&](const char* what) {
+        if (!trace) return;
+        const double t = now();
+        fprintf(stderr, "tlpb200 setup:   %-20s %8.3f s\n", what, t - t_mark);
+        t_mark = t;
+    };
 
     // 1. fill-reducing ordering
     std::vector<int32_t> perm1;
@@ -215,6 +227,7 @@ void analyze_pattern(const SymPattern& P0, const SymOptions& opt, const int8_t* 
         if (perm1[k] < 0 || perm1[k] >= N || ip1[perm1[k]] != -1) throw std::runtime_error("ordering is not a permutation");
         ip1[perm1[k]] = k;
     }
+    lap("ordering (AMD)");
     SymPattern P1 = permute_pattern(P0, ip1);
 
     // 2. etree + postorder, composed into the permutation
@@ -231,8 +244,10 @@ void analyze_pattern(const SymPattern& P0, const SymOptions& opt, const int8_t* 
     for (int32_t v = 0; v < N; ++v)
         if (par1[v] >= 0) S.parent[ipost[v]] = ipost[par1[v]];
 
+    lap("etree + postorder");
     // 3. column counts
     S.colcount = column_counts(Pp, S.parent);
+    lap("column counts");
     S.nnzL = 0;
     S.flops = 0.0;
     for (int32_t j = 0; j < N; ++j) { S.nnzL += S.colcount[j]; S.flops += (double)S.colcount[j] * (double)S.colcount[j]; }
@@ -298,6 +313,7 @@ void analyze_pattern(const SymPattern& P0, const SymOptions& opt, const int8_t* 
     S.col2sn.resize(N);
     for (int32_t s = 0; s < ns; ++s) for (int32_t j = first[s]; j < first[s + 1]; ++j) S.col2sn[j] = s;
 
+    lap("supernodes + relax");
     // 6. supernodal row structure: rows(s) = own columns, then sorted union of
     //    {pattern rows >= last col} and {children's below rows} minus own columns
     S.sn_parent.assign(ns, -1);
@@ -334,6 +350,7 @@ void analyze_pattern(const SymPattern& P0, const SymOptions& opt, const int8_t* 
         }
     }
 
+    lap("row structure");
     // 7. panel storage
     S.sn_xptr.assign(ns + 1, 0);
     S.max_ncol = S.max_nrow = 0;

@@ -304,14 +304,16 @@ class B200KKTSolver:
     def update_plan(self):
         """Update-task plan (host data, available on analyze_only handles): FP64 tile tasks, tcgen05 tasks, pieces, views."""
         lib = _lib.load()
-        cnt = np.zeros(5, np.int64)
-        lib.tlpb200_debug_update_plan(self._h, cnt.ctypes.data_as(C.POINTER(C.c_int64)), None, None, None, None, None)
+        cnt = np.zeros(8, np.int64)
+        lib.tlpb200_debug_update_plan(self._h, cnt.ctypes.data_as(C.POINTER(C.c_int64)), None, None, None, None, None, None, None)
         upd = np.zeros((int(cnt[0]), 8), np.int32); upd128 = np.zeros((int(cnt[1]), 8), np.int32)
         oz = np.zeros((int(cnt[2]), 8), np.int32); pieces = np.zeros((int(cnt[3]), 4), np.int32)
-        views = np.zeros((int(cnt[4]), 4), np.int32)
+        views = np.zeros((int(cnt[4]), 4), np.int32); panel = np.zeros((int(cnt[5]), 4), np.int32)
+        levels = np.zeros((int(cnt[6]), int(cnt[7])), np.int32)
         vp = lambda a: C.c_void_p(a.ctypes.data)
-        lib.tlpb200_debug_update_plan(self._h, cnt.ctypes.data_as(C.POINTER(C.c_int64)), vp(upd), vp(upd128), vp(oz), vp(pieces), vp(views))
-        return {"upd": upd, "upd128": upd128, "oz": oz, "pieces": pieces, "views": views}
+        lib.tlpb200_debug_update_plan(self._h, cnt.ctypes.data_as(C.POINTER(C.c_int64)), vp(upd), vp(upd128), vp(oz), vp(pieces), vp(views),
+                                      vp(panel), vp(levels))
+        return {"upd": upd, "upd128": upd128, "oz": oz, "pieces": pieces, "views": views, "panel": panel, "levels": levels}
 
     def big_plan(self):
         """Dense-solve plan of the big supernodes (host data, available on analyze_only handles)."""
