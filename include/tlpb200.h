@@ -90,6 +90,9 @@ typedef struct tlpb200_stats {
 } tlpb200_stats;
 
 void tlpb200_default_options(tlpb200_options* opt);
+/* out[0] = sizeof(tlpb200_options), out[1] = sizeof(tlpb200_stats), out[2] = TLPB200_NCLASS: lets a binding (the ctypes mirror in
+ * tulip.jl_b200/_lib.py, the Julia structs in tulip.jl_b200/julia/TlpB200.jl) check its struct layouts against the library. */
+void tlpb200_abi_sizes(int32_t* out);
 
 /* KKT.setup(A, system, backend)  (KKT.jl:59; Cholmod/spd.jl:5-20, sqd.jl:5-22):
  * symbolic analysis on the host, plan + matrix upload to the device. */

@@ -28,6 +28,22 @@ def test_library_exports_every_declared_symbol():
     assert sorted(_lib.SYMBOLS) == declared
 
 
+def test_binding_struct_layouts_match_the_library():
+    """the ctypes mirrors (and, by the same field lists, the Julia structs of tulip.jl_b200/julia/TlpB200.jl) must have the
+    sizes the compiled library uses for tlpb200_options / tlpb200_stats"""
+    import ctypes as C
+    lib = _lib.load()
+    out = (C.c_int32 * 3)()
+    lib.tlpb200_abi_sizes(out)
+    assert out[0] == C.sizeof(_lib.Options) == 16 * 4
+    assert out[1] == C.sizeof(_lib.Stats)
+    assert out[2] == 24 and len(_lib.KERNEL_CLASSES) <= out[2]
+    jl = open(os.path.join(ROOT, "tulip.jl_b200", "julia", "TlpB200.jl")).read()
+    body = jl[jl.index("struct COptions"):jl.index("end", jl.index("struct COptions"))]
+    n32 = len(re.findall(r"::Int32", body)) + sum(int(x) for x in re.findall(r"NTuple\{(\d+),Int32\}", body))
+    assert n32 * 4 == out[0], "Julia COptions does not match sizeof(tlpb200_options)"
+
+
 def test_backend_strings():
     assert "TlpB200" in pkg.backend(None)
 

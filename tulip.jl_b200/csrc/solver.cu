@@ -1382,6 +1382,13 @@ int tlpb200_get_dense_cols(const tlpb200_solver* s, int32_t* count, int64_t* col
     return TLPB200_OK;
 }
 
+void tlpb200_abi_sizes(int32_t* out) {
+    if (!out) return;
+    out[0] = (int32_t)sizeof(tlpb200_options);
+    out[1] = (int32_t)sizeof(tlpb200_stats);
+    out[2] = TLPB200_NCLASS;
+}
+
 const char* tlpb200_last_error(const tlpb200_solver* s) { return s ? s->err.c_str() : "null solver"; }
 const char* tlpb200_backend_name(void) { return "TlpB200 (supernodal signed Cholesky, CUDA sm_100a)"; }
 const char* tlpb200_linear_system(const tlpb200_solver* s) {
