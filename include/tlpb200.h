@@ -153,9 +153,10 @@ int tlpb200_debug_ozaki(const double* P, int64_t R, int64_t K, double* C, int32_
 /* Update-task plan as int32 records (host data, also on analyze_only handles): upd / upd128 = FP64 tile tasks
  * {piece, i0, ni, k0, nk, tgt, diag, pad}, oz = tcgen05 tasks {view, rbA, rbB, half, k0, k1, pad, pad}, pieces =
  * {sn, c0, c1, level}, views = {sn, nrb, ncb, base_level}, panel = trsm row tiles {piece, r0, nr, pad}, levels = the
- * per-level ranges (LevelPlan, counts[7] int32 each); counts[0..6] = their lengths.  NULL arrays are skipped. */
+ * per-level ranges (LevelPlan, counts[7] int32 each), small_list / level_pieces = the one-CTA supernodes / pieces grouped by
+ * level; counts[0..6], counts[8], counts[9] = their lengths (counts has 10 entries).  NULL arrays are skipped. */
 int tlpb200_debug_update_plan(const tlpb200_solver* s, int64_t* counts, int32_t* upd, int32_t* upd128, int32_t* oz, int32_t* pieces,
-                              int32_t* views, int32_t* panel, int32_t* levels);
+                              int32_t* views, int32_t* panel, int32_t* levels, int32_t* small_list, int32_t* level_pieces);
 int tlpb200_debug_big_plan(const tlpb200_solver* s, int64_t* counts, void* pack, void* fwd, void* bwd);
 
 /* ---- multi-GPU, one process per GPU (no counterpart in the reference, NEWS.md:31) -------------

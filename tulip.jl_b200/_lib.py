@@ -117,7 +117,7 @@ def load():
     lib.tlpb200_debug_factor_trace.restype = C.c_int
     lib.tlpb200_abi_sizes.argtypes = [C.POINTER(C.c_int32)]
     lib.tlpb200_abi_sizes.restype = None
-    lib.tlpb200_debug_update_plan.argtypes = [p, C.POINTER(C.c_int64), p, p, p, p, p, p, p]
+    lib.tlpb200_debug_update_plan.argtypes = [p, C.POINTER(C.c_int64), p, p, p, p, p, p, p, p, p]
     lib.tlpb200_debug_update_plan.restype = C.c_int
     lib.tlpb200_debug_ozaki.argtypes = [dp, C.c_int64, C.c_int64, dp, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_int32)]
     lib.tlpb200_debug_ozaki.restype = C.c_int

@@ -1191,7 +1191,7 @@ int tlpb200_debug_big_plan(const tlpb200_solver* s, int64_t* counts, void* pack,
 // (piece, target entry) pair exactly once).  Arrays are int32 records: upd / upd128 = UpdTask (8), oz = OzTask (8),
 // pieces = Piece (4), views = {sn, nrb, ncb, base_level}.
 int tlpb200_debug_update_plan(const tlpb200_solver* s, int64_t* counts, int32_t* upd, int32_t* upd128, int32_t* oz, int32_t* pieces,
-                              int32_t* views, int32_t* panel, int32_t* levels) {
+                              int32_t* views, int32_t* panel, int32_t* levels, int32_t* small_list, int32_t* level_pieces) {
     if (!s) return TLPB200_BAD_ARG;
     const Plan& P = s->plan;
     static_assert(sizeof(UpdTask) == 32 && sizeof(OzTask) == 32 && sizeof(Piece) == 16 && sizeof(PanelTask) == 16, "record sizes");
@@ -1205,7 +1205,11 @@ int tlpb200_debug_update_plan(const tlpb200_solver* s, int64_t* counts, int32_t*
         counts[5] = (int64_t)P.panel.size();
         counts[6] = (int64_t)P.levels.size();
         counts[7] = (int64_t)(sizeof(LevelPlan) / sizeof(int32_t));
+        counts[8] = (int64_t)P.small_list.size();
+        counts[9] = (int64_t)P.level_pieces.size();
     }
+    if (small_list && !P.small_list.empty()) std::memcpy(small_list, P.small_list.data(), P.small_list.size() * sizeof(int32_t));
+    if (level_pieces && !P.level_pieces.empty()) std::memcpy(level_pieces, P.level_pieces.data(), P.level_pieces.size() * sizeof(int32_t));
     if (panel && !P.panel.empty()) std::memcpy(panel, P.panel.data(), P.panel.size() * sizeof(PanelTask));
     if (levels && !P.levels.empty()) std::memcpy(levels, P.levels.data(), P.levels.size() * sizeof(LevelPlan));
     if (upd && !P.upd.empty()) std::memcpy(upd, P.upd.data(), P.upd.size() * sizeof(UpdTask));

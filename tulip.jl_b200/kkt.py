@@ -304,16 +304,25 @@ class B200KKTSolver:
     def update_plan(self):
         """Update-task plan (host data, available on analyze_only handles): FP64 tile tasks, tcgen05 tasks, pieces, views."""
         lib = _lib.load()
-        cnt = np.zeros(8, np.int64)
-        lib.tlpb200_debug_update_plan(self._h, cnt.ctypes.data_as(C.POINTER(C.c_int64)), None, None, None, None, None, None, None)
+        cnt = np.zeros(10, np.int64)
+        none9 = [None] * 9
+        lib.tlpb200_debug_update_plan(self._h, cnt.ctypes.data_as(C.POINTER(C.c_int64)), *none9)
         upd = np.zeros((int(cnt[0]), 8), np.int32); upd128 = np.zeros((int(cnt[1]), 8), np.int32)
         oz = np.zeros((int(cnt[2]), 8), np.int32); pieces = np.zeros((int(cnt[3]), 4), np.int32)
         views = np.zeros((int(cnt[4]), 4), np.int32); panel = np.zeros((int(cnt[5]), 4), np.int32)
         levels = np.zeros((int(cnt[6]), int(cnt[7])), np.int32)
+        small_list = np.zeros(int(cnt[8]), np.int32); level_pieces = np.zeros(int(cnt[9]), np.int32)
         vp = lambda a: C.c_void_p(a.ctypes.data)
         lib.tlpb200_debug_update_plan(self._h, cnt.ctypes.data_as(C.POINTER(C.c_int64)), vp(upd), vp(upd128), vp(oz), vp(pieces), vp(views),
-                                      vp(panel), vp(levels))
-        return {"upd": upd, "upd128": upd128, "oz": oz, "pieces": pieces, "views": views, "panel": panel, "levels": levels}
+                                      vp(panel), vp(levels), vp(small_list), vp(level_pieces))
+        return {"upd": upd, "upd128": upd128, "oz": oz, "pieces": pieces, "views": views, "panel": panel, "levels": levels,
+                "small_list": small_list, "level_pieces": level_pieces}
+
+    # field order of the int32 records of update_plan()["levels"] (LevelPlan in csrc/plan.hpp)
+    LEVEL_FIELDS = ("small_begin", "small_end", "piece_begin", "piece_end", "panel_begin", "panel_end", "panel_crit_end",
+                    "ext_begin", "ext_end", "ext_crit_end", "urgent_end", "lazy_begin", "lazy_end", "ext_atomic",
+                    "fwd_begin", "fwd_end", "bwd_begin", "bwd_end", "fbig_begin", "fbig_end", "bbig_begin", "bbig_end",
+                    "below_begin", "below_end", "oz_begin", "oz_end", "ozs_begin", "ozs_end", "oz_tile", "inv_end", "pack_end")
 
     def big_plan(self):
         """Dense-solve plan of the big supernodes (host data, available on analyze_only handles)."""
