@@ -15,17 +15,35 @@ pkg = tlpb200_loader.load()
 from tulip_jl_b200 import lpgen  # noqa: E402
 
 
-def _emulate(A, backend_kwargs, theta_seed=0):
+def _signed_chol(B, sg):
+    """B = L diag(sg) L' without pivoting (the signed Cholesky of DESIGN 1; plain Cholesky when sg = +1)."""
+    w = B.shape[0]
+    L = np.zeros_like(B)
+    for j in range(w):
+        dj = B[j, j] - (L[j, :j] ** 2) @ sg[:j]
+        assert dj * sg[j] > 0
+        L[j, j] = np.sqrt(dj * sg[j])
+        if j + 1 < w:
+            L[j + 1:, j] = (B[j + 1:, j] - (L[j + 1:, :j] * sg[:j]) @ L[j, :j]) / (sg[j] * L[j, j])
+    return L
+
+
+def _emulate(A, backend_kwargs, theta_seed=0, system="K1"):
     A = sp.csc_matrix(A)
     m, n = A.shape
-    k = pkg.setup(A, pkg.K1(), pkg.Backend(analyze_only=True, **backend_kwargs))
+    k = pkg.setup(A, pkg.K1() if system == "K1" else pkg.K2(), pkg.Backend(analyze_only=True, **backend_kwargs))
     plan, sym = k.update_plan(), k.symbolic()
     LF = {f: i for i, f in enumerate(k.LEVEL_FIELDS)}
     assert plan["levels"].shape[1] == len(LF)
     rng = np.random.default_rng(theta_seed)
     d = 1.0 / np.exp(rng.uniform(-2, 2, n))
-    K = (A @ sp.diags(d) @ A.T + sp.diags(np.full(m, 1e-3))).toarray()
     p = sym["perm"]
+    if system == "K1":
+        K = (A @ sp.diags(d) @ A.T + sp.diags(np.full(m, 1e-3))).toarray()
+        sg = np.ones(m)
+    else:                                                   # systems.jl:8-32: [-(Theta^-1 + Rp)  A'; A  Rd]
+        K = sp.bmat([[sp.diags(-(1.0 / d + 1e-3)), A.T], [A, sp.diags(np.full(m, 1e-3))]]).toarray()
+        sg = np.where(p < n, -1.0, 1.0)                     # expected pivot signs in permuted order
     Kp = K[np.ix_(p, p)]
     W = np.tril(Kp).copy()
     first, rp, rows_all = sym["sn_first"], sym["sn_rowptr"], sym["sn_rows"]
@@ -37,7 +55,7 @@ def _emulate(A, backend_kwargs, theta_seed=0):
         s, c0, c1, _lvl = (int(x) for x in pieces[piece])
         r = rows_of(s)
         I, Kc = r[i0:i0 + ni], r[k0:k0 + nk]
-        upd = W[np.ix_(I, np.arange(c0, c1))] @ W[np.ix_(Kc, np.arange(c0, c1))].T
+        upd = (W[np.ix_(I, np.arange(c0, c1))] * sg[c0:c1]) @ W[np.ix_(Kc, np.arange(c0, c1))].T
         if diag:
             upd = np.tril(upd)
         W[np.ix_(I, Kc)] -= upd
@@ -71,12 +89,12 @@ def _emulate(A, backend_kwargs, theta_seed=0):
             f, l = int(first[s]), int(first[s + 1])
             r = rows_of(s)
             below = r[l - f:]
-            L11 = np.linalg.cholesky(W[f:l, f:l] + np.tril(W[f:l, f:l], -1).T)
+            L11 = _signed_chol(W[f:l, f:l] + np.tril(W[f:l, f:l], -1).T, sg[f:l])
             W[f:l, f:l] = L11
-            if len(below):
-                L21 = sla.solve_triangular(L11, W[np.ix_(below, np.arange(f, l))].T, lower=True).T
+            if len(below):                                   # X = A21 L11^-T S
+                L21 = sla.solve_triangular(L11, W[np.ix_(below, np.arange(f, l))].T, lower=True).T * sg[f:l]
                 W[np.ix_(below, np.arange(f, l))] = L21
-                W[np.ix_(below, below)] -= np.tril(L21 @ L21.T)
+                W[np.ix_(below, below)] -= np.tril((L21 * sg[f:l]) @ L21.T)
         for pc in plan["level_pieces"][g("piece_begin"):g("piece_end")]:   # k_diag_factor + k_trsm
             s, c0, c1, lvl = (int(x) for x in pieces[int(pc)])
             assert lvl == L
@@ -84,10 +102,10 @@ def _emulate(A, backend_kwargs, theta_seed=0):
             r = rows_of(s)
             below = r[c1 - f:]
             blk = W[c0:c1, c0:c1]
-            L11 = np.linalg.cholesky(blk + np.tril(blk, -1).T)
+            L11 = _signed_chol(blk + np.tril(blk, -1).T, sg[c0:c1])
             W[c0:c1, c0:c1] = L11
             if len(below):
-                W[np.ix_(below, np.arange(c0, c1))] = sla.solve_triangular(L11, W[np.ix_(below, np.arange(c0, c1))].T, lower=True).T
+                W[np.ix_(below, np.arange(c0, c1))] = sla.solve_triangular(L11, W[np.ix_(below, np.arange(c0, c1))].T, lower=True).T * sg[c0:c1]
         for T in plan["upd"][g("ext_begin"):g("ext_end")]:                 # urgent tiles (k_update)
             apply_tile(T)
         if g("lazy_end") > g("lazy_begin"):
@@ -101,7 +119,7 @@ def _emulate(A, backend_kwargs, theta_seed=0):
     for q in sorted(pending_oz):
         for T in pending_oz[q][0]:
             apply_oz(T, pending_oz[q][1])
-    Lref = np.linalg.cholesky(Kp)
+    Lref = _signed_chol(Kp, sg)
     return W, Lref, k.stats()
 
 
@@ -117,4 +135,14 @@ def test_level_schedule_sparse_staircase_k1():
     """many small supernodes, ancestors updated through the segment lists (no dense root)"""
     lp = lpgen.banded_random(900, 1800, 4, 64, seed=99, name="band")
     W, Lref, _ = _emulate(lp.A, dict(ozaki_ncol=-1))
+    assert np.abs(W - Lref).max() <= 1e-9 * np.abs(Lref).max()
+
+
+def test_level_schedule_k2_signed_factor():
+    """K2 (sqd.jl:24-55): quasi-definite augmented matrix, signed Cholesky L S L' with the x-block pivots negative"""
+    lp = lpgen.config(3, mini=True)
+    W, Lref, _ = _emulate(lp.A, dict(), system="K2")
+    assert np.abs(W - Lref).max() <= 1e-9 * np.abs(Lref).max()
+    lp = lpgen.banded_random(300, 600, 4, 48, seed=5, name="band2")
+    W, Lref, _ = _emulate(lp.A, dict(), system="K2")
     assert np.abs(W - Lref).max() <= 1e-9 * np.abs(Lref).max()
