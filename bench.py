@@ -10,22 +10,30 @@ the reference's caller (tulip.jl_b200/hsd.py <- src/IPM/HSD/step.jl).  The refer
 same quantity out of its TimerOutputs sections "Factorization" + "KKT" (plan A):
 iterations/s = niter / (sum Factorization + sum KKT).
 
+* default workload (``--config auto``): N = 1 -> config T, the north-star LP of BASELINE.json (m=1e5, n=2e5,
+             nnz 1.1e6, K1; it fits one GPU); N > 1 -> config 4 (block-angular), the only BASELINE config whose
+             elimination tree shards: subtrees over the ranks + separator reduce, scaling = "strong"; rank 0 first
+             times the same workload on one GPU (``n1_same_workload``).  The other configs (2, 3, 5, mini) are
+             selected with ``--config``; with N > 1 they run as independent replicas (scaling = "weak").
 * ``e2e``  : the steps timed through the reference-facing host-pointer API (``KKT.update!`` /
              ``KKT.solve!`` with host vectors; H2D/D2H copies and syncs inside the timed region).
 * ``value``: the same steps replayed with all inputs resident in HBM (``*_dev`` entry points),
              CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.
-* N > 1    : config 2 does not shard ("replicas only"): every rank runs an independent
-             replica, value = N * steps / max-over-ranks time, scaling = "weak".
+* the IPM runs to convergence (reference default IterationsLimit = 100); when it needs fewer than W + K
+             iterations the timed window cycles over the recorded post-warm-up iterations (``steps_real``).
 * ``--impl reference``: the oracle's CPU port of the reference path (oracle/cpu_kkt.py: SciPy
              SpGEMM assemble as in spd.jl:43 + own supernodal Cholesky on OpenBLAS, all host
              threads) driven by the oracle's HSD restatement -- NOT CHOLMOD (no Julia/SuiteSparse
-             in the image).
+             in the image).  On config T the CPU arm runs ONE real iteration (1 update! + its solves: minutes of
+             host time), on the other configs the whole IPM.  Its result is cached in /tmp so that the GPU arm, run
+             afterwards on the same box, quotes it as ``cpu_baseline`` and compares objectives with it.
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
+import socket
 import subprocess
 import sys
 import threading
@@ -38,36 +46,44 @@ import numpy as np  # noqa: E402
 
 METRIC = "IPM iterations/sec (KKT factor+solve)"
 UNIT = "iter/s"
+CPU_LABEL = ("CPU port: SciPy SpGEMM assemble + own left-looking supernodal Cholesky on SciPy-OpenBLAS -- NOT Tulip/CHOLMOD "
+             "(no Julia/SuiteSparse in the image)")
+ONE_ITER_ABOVE_FLOPS = 5e12     # CPU arm: beyond this a factorisation takes minutes -> ONE real iteration instead of the whole IPM
 
 
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+CONFIGS = {"2": (2, False, "K1"), "3": (3, False, "K2"), "4": (4, False, "K1"), "5": (5, False, "K1"), "T": ("T", False, "K1"),
+           "mini": (2, True, "K1"), "3mini": (3, True, "K2"), "4mini": (4, True, "K1"), "5mini": (5, True, "K1"), "Tmini": ("T", True, "K1")}
+
+
 def build_lp(cfg):
     import tlpb200_loader
     pkg = tlpb200_loader.load()
     from tulip_jl_b200 import lpgen
-    if cfg == "2":
-        return pkg, lpgen.config(2), "K1"
-    if cfg == "3":
-        return pkg, lpgen.config(3), "K2"
-    if cfg == "4":
-        return pkg, lpgen.config(4), "K1"
-    if cfg == "4mini":
-        return pkg, lpgen.config(4, mini=True), "K1"
-    if cfg == "T":
-        return pkg, lpgen.config("T"), "K1"
-    if cfg == "mini":
-        return pkg, lpgen.config(2, mini=True), "K1"
-    raise SystemExit(f"unknown --config {cfg}")
+    if cfg not in CONFIGS:
+        raise SystemExit(f"unknown --config {cfg}")
+    num, mini, sysname = CONFIGS[cfg]
+    return pkg, lpgen.config(num, mini=mini), sysname
 
 
-def workload_name(lp, sysname, nsolve):
+def workload_name(lp, sysname):
     md = lp.meta
     return (f"{lp.name}: {md.get('kind')} LP m={md['m']} n={md['n']} nnz(A)={md['nnz']}, {sysname} "
-            f"({'normal equations Cholesky' if sysname == 'K1' else 'augmented LDLt'}); step = 1 update! + "
-            f"{nsolve:.2f} solve! (mean over timed HSD iterations)")
+            f"({'normal equations Cholesky' if sysname == 'K1' else 'augmented LDLt'}); step = 1 update! + its solve! calls "
+            f"of one HSD iteration")
+
+
+# config 5 (8 dense columns): the reference has no dense-column handling -- its K1 (spd.jl:43) would form a fully dense
+# A D A' (10 GB factor, ~1 min per CPU factorisation) -- so the CPU arm runs this LP the way Tulip runs it by default,
+# with the augmented system K2 (KKT.jl:134-137), which is the faster CPU choice (conservative for the speed-up quoted).
+CPU_SYSTEM = {"5": "K2", "5mini": "K2"}
+
+
+def cache_path(cfg):
+    return os.path.join("/tmp", f"tlpb200_cpu_port_cfg{cfg}.json")
 
 
 class ClockSampler:
@@ -104,7 +120,7 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             pass
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for s in self.samples:
             f = [x.strip() for x in s.split(",")]
@@ -114,11 +130,15 @@ class ClockSampler:
                 sm.append(float(f[0])); mx.append(float(f[1]))
             except ValueError:
                 continue
+            try:
+                pw.append(float(f[2]))
+            except ValueError:
+                pass
             for nm, v in zip(names, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "power_w_median": float(np.median(pw)) if pw else None}
 
 
 def measured_peaks():
@@ -131,9 +151,39 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback (B200_PROFILING.md)"
 
 
+def ipm_summary(h):
+    """final objective / residual figures of an HSD run (either the host mirror or the oracle restatement):
+    log rows are (iter, pobj, dobj, pfeas, dfeas, gfeas, mu), the last one belongs to the final iterate."""
+    it, pobj, dobj, pf, df, gf, mu = h.log[-1]
+    out = {"status": h.status, "iters": int(h.niter), "pobj": float(pobj), "dobj": float(dobj),
+           "rel_gap": float(abs(pobj - dobj) / (1.0 + abs(dobj))), "pfeas": float(pf), "dfeas": float(df), "mu": float(mu)}
+    if len(h.log) > 1:
+        _, p1, d1, _, _, _, mu1 = h.log[1]
+        out["after_iter1"] = {"pobj": float(p1), "dobj": float(d1), "mu": float(mu1)}
+    return out
+
+
+def objective_parity(mine, ref):
+    """relative differences between this arm's objectives and the CPU arm's (same LP, same algorithm, different KKT backend)"""
+    if ref is None:
+        return None
+    rel = lambda a, b: float(abs(a - b) / max(1.0, abs(b)))
+    out = {}
+    if ref.get("status") == mine.get("status") == "Trm_Optimal":
+        out["final_pobj_rel_diff"] = rel(mine["pobj"], ref["pobj"])
+        out["final_dobj_rel_diff"] = rel(mine["dobj"], ref["dobj"])
+        out["final_within_1e-8"] = bool(out["final_pobj_rel_diff"] <= 1e-8 and out["final_dobj_rel_diff"] <= 1e-8)
+    if "after_iter1" in ref and "after_iter1" in mine:
+        out["iter1_pobj_rel_diff"] = rel(mine["after_iter1"]["pobj"], ref["after_iter1"]["pobj"])
+        out["iter1_dobj_rel_diff"] = rel(mine["after_iter1"]["dobj"], ref["after_iter1"]["dobj"])
+        out["iter1_within_1e-8"] = bool(out["iter1_pobj_rel_diff"] <= 1e-8 and out["iter1_dobj_rel_diff"] <= 1e-8)
+    out["reference_ipm"] = {k: ref.get(k) for k in ("status", "iters", "pobj", "dobj", "after_iter1")}
+    return out
+
+
 def record_hsd(pkg, lp, kkt, niter):
-    """Run the HSD mirror for `niter` iterations through the host API, recording every KKT input
-    and timing every KKT call.  Returns per-iteration records."""
+    """Run the HSD mirror for at most `niter` iterations through the host API, recording every KKT input
+    and timing every KKT call.  Returns the driver and the per-iteration records."""
     from tulip_jl_b200 import hsd
     recs = []
     cur = {}
@@ -142,11 +192,15 @@ def record_hsd(pkg, lp, kkt, niter):
         m, n = kkt.m, kkt.n
 
         def update(self, th, rp, rd):
+            # a regularisation bump (step.jl:34-51) repeats update!: the record keeps the successful inputs and ALL the time
+            t_prev = cur.get("t_update", 0.0) if cur.get("open") else 0.0
             cur.clear()
-            cur.update(theta=th.copy(), regP=rp.copy(), regD=rd.copy(), rhs=[], t_update=0.0, t_solve=0.0)
+            cur.update(theta=th.copy(), regP=rp.copy(), regD=rd.copy(), rhs=[], t_update=t_prev, t_solve=0.0, open=True)
             t0 = time.perf_counter()
-            kkt.update(th, rp, rd)
-            cur["t_update"] = time.perf_counter() - t0
+            try:
+                kkt.update(th, rp, rd)
+            finally:
+                cur["t_update"] += time.perf_counter() - t0
 
         def solve(self, dx, dy, xp, xd):
             cur["rhs"].append((np.array(xp, copy=True), np.array(xd, copy=True)))
@@ -154,9 +208,35 @@ def record_hsd(pkg, lp, kkt, niter):
             kkt.solve(dx, dy, xp, xd)
             cur["t_solve"] += time.perf_counter() - t0
 
+    def done(hh):
+        cur["open"] = False
+        recs.append(dict(cur))
+
     h = hsd.HSD(lp.A, lp.b, lp.c, lp.l, lp.u, Rec())
-    h.optimize(max_iter=niter, callback=lambda hh: recs.append(dict(cur)))
+    h.optimize(max_iter=niter, callback=done)
     return h, recs
+
+
+def timed_window(recs, W, K):
+    """K records after W warm-up ones; cycles over the post-warm-up iterations when the IPM converged earlier"""
+    base = len(recs)
+    if base < W + 1:
+        raise SystemExit(f"IPM terminated after {base} iterations, inside the warm-up; lower --warmup")
+    out = list(recs)
+    while len(out) < W + K:
+        out.append(recs[W + (len(out) - base) % (base - W)])
+    return out[:W + K], min(K, base - W)
+
+
+def read_cpu_cache(cfg):
+    """the CPU arm's result if `bench.py --impl reference` ran on this box within the last 6 hours"""
+    try:
+        d = json.load(open(cache_path(cfg)))
+        if d.get("host") == socket.gethostname() and time.time() - d.get("when", 0) < 6 * 3600:
+            return d
+    except Exception:
+        pass
+    return None
 
 
 def gpu_arm(args):
@@ -172,37 +252,43 @@ def gpu_arm(args):
         import torch.distributed as dist_
         dist = dist_
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-    pkg, lp, sysname = build_lp(args.config)
+    cfg = args.config
+    if cfg == "auto":
+        cfg = "T" if world == 1 else "4"
+    pkg, lp, sysname = build_lp(cfg)
     A = lp.A
     m, n = A.shape
     sy = pkg.K1() if sysname == "K1" else pkg.K2()
     K, W = args.steps, args.warmup
-    if world > 1 and args.config.startswith("4"):
-        return sharded_arm(args, pkg, lp, sysname, sy, dist, rank, world, local)
+    if world > 1 and cfg.startswith("4"):
+        return sharded_arm(args, cfg, pkg, lp, sysname, sy, dist, rank, world, local)
     t0 = time.time()
     kkt = pkg.setup(A, sy, pkg.Backend(device=local))
     t_setup = time.time() - t0
-    # ---- pass 1: the real IPM through the host API (e2e) ------------------------------------
+    # ---- pass 1: the real IPM through the host API (e2e), run to convergence -------------------
     sampler = ClockSampler(local)
-    h, recs = record_hsd(pkg, lp, kkt, W + K)
-    if len(recs) < W + 1:
-        raise SystemExit("IPM terminated during warm-up; lower --warmup")
-    base = len(recs)
-    while len(recs) < W + K:                # converged early: keep cycling over the recorded iterations
-        recs.append(recs[W + (len(recs) - base) % (base - W)])
-    timed = recs[W:W + K]
+    h, recs = record_hsd(pkg, lp, kkt, max(args.ipm_limit, W + K) if args.ipm_limit > 0 else W + K)
+    win, k_real = timed_window(recs, W, K)
+    timed = win[W:W + K]
     nsolve = float(np.mean([len(r["rhs"]) for r in timed]))
     e2e_time = sum(r["t_update"] + r["t_solve"] for r in timed)
     h2d = float(np.mean([(2 * n + m) * 8 + len(r["rhs"]) * (n + m) * 8 for r in timed]))
     d2h = float(np.mean([4 + len(r["rhs"]) * (n + m) * 8 for r in timed]))
     st0 = kkt.stats()
+    ipm = ipm_summary(h)
     # ---- pass 2: device-resident replay (value) ---------------------------------------------
     dev = torch.device(f"cuda:{local}")
     stream = torch.cuda.current_stream()
     kkt.set_stream(stream.cuda_stream)
     tt = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
-    dev_recs = [dict(theta=tt(r["theta"]), regP=tt(r["regP"]), regD=tt(r["regD"]),
-                     rhs=[(tt(xp), tt(xd)) for xp, xd in r["rhs"]]) for r in recs[:W + K]]
+    cache = {}
+
+    def dev_rec(r):
+        if id(r) not in cache:
+            cache[id(r)] = dict(theta=tt(r["theta"]), regP=tt(r["regP"]), regD=tt(r["regD"]), rhs=[(tt(xp), tt(xd)) for xp, xd in r["rhs"]])
+        return cache[id(r)]
+
+    dev_recs = [dev_rec(r) for r in win]
     ddx = torch.zeros(n, dtype=torch.float64, device=dev)
     ddy = torch.zeros(m, dtype=torch.float64, device=dev)
 
@@ -235,7 +321,7 @@ def gpu_arm(args):
     # ---- pass 3: per-kernel-class profile of one step (roofline numerators) -------------------
     kkt.set_stream(0)
     kkt.set_profiling(True)
-    r = recs[W]
+    r = win[W]
     kkt.update(r["theta"], r["regP"], r["regD"])
     dx = np.zeros(n); dy = np.zeros(m)
     kkt.solve(dx, dy, r["rhs"][0][0], r["rhs"][0][1])
@@ -254,43 +340,47 @@ def gpu_arm(args):
         s0.record(); torch.matmul(a, b); s1.record(); torch.cuda.synchronize()
         best = min(best, s0.elapsed_time(s1))
     dgemm_tf = 2 * 4096 ** 3 / (best * 1e-3) / 1e12
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "k_update_traffic.json")
-    if os.path.exists(tp):
+    del a, b
+
+    def traffic_of(name):
+        tp = os.path.join(ROOT, "profiles", name)
         try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            return json.load(open(tp)).get("dram_bytes_per_launch")
         except Exception:
-            traffic = None
+            return None
+
+    ms_fac = max(1e-9, sp["ms_assemble"] + sp["ms_factor"])
     ach = flops_upd / (ms_upd * 1e-3) / 1e12 if ms_upd > 0 else 0.0
     roofline_dmma = {"kernel": "k_update (FP64 DMMA m8n8k4 tile update: supernode SYRK/GEMM + scatter)",
                      "bound": "tensor", "achieved": round(ach, 3), "peak": round(dgemm_tf, 2), "unit": "TFLOP/s",
-                     "frac": round(ach / dgemm_tf, 4) if dgemm_tf > 0 else None, "traffic": traffic,
+                     "frac": round(ach / dgemm_tf, 4) if dgemm_tf > 0 else None, "traffic": traffic_of("k_update_traffic.json"),
                      "peak_source": "cuBLAS DGEMM 4096^3 measured live in this run (MEASURED_PEAKS.json has no FP64 figure; nominal B200 FP64 = 40 TFLOP/s)",
                      "launches_per_step": int(n_upd), "avg_launch_ms": round(ms_upd / max(1, n_upd), 4),
-                     "algorithmic_flops_per_step": flops_upd, "share_of_update_ms": round(ms_upd / max(1e-9, sp["ms_assemble"] + sp["ms_factor"]), 3)}
+                     "algorithmic_flops_per_step": flops_upd, "share_of_update_ms": round(ms_upd / ms_fac, 3)}
     ms_oz, n_oz = cls["oz_update"]
     if n_oz > 0 and sp["flops_update_oz"] > 0:
         # dominant kernel: the tcgen05 int8 (Ozaki) update.  One FP64 multiply-add = 36 int8 digit-plane multiply-adds, so
-        # the algorithmic tensor work is 36 x the FP64 flops; peak = dense int8 rate = 2 x the measured dense bf16 rate
-        # (B200: 4.5 vs 2.25 POP/s nominal), burst figure because profiling mode times every launch alone.
-        int8_peak = 2.0 * float(peaks.get("bf16_tflops", 1590.0))
+        # the algorithmic tensor work is 36 x the FP64 flops of the tasks' tiles; peak = dense int8 rate = 2 x the measured
+        # dense bf16 rate (B200: 4.5 vs 2.25 POP/s nominal).  `frac` uses the BURST figure (conservative); a launch of a
+        # multi-second step runs at the sustained rate, reported as frac_vs_sustained.  frac_structural counts only the
+        # structural flops sum_j c_j^2 share of the tiles (relaxed amalgamation pads the big supernodes with explicit zeros).
+        int8_burst = 2.0 * float(peaks.get("bf16_tflops", 1590.0))
+        int8_sust = 2.0 * float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
         tops = 36.0 * sp["flops_update_oz"] / (ms_oz * 1e-3) / 1e12
-        tp2 = os.path.join(ROOT, "profiles", "k_oz_update_traffic.json")
-        traffic_oz = None
-        if os.path.exists(tp2):
-            try:
-                traffic_oz = json.load(open(tp2)).get("dram_bytes_per_launch")
-            except Exception:
-                traffic_oz = None
+        tile_flops = sp["flops_update_oz"] + sp["flops_update_ext"] + sp["flops_update_inner"]
+        structural_share = min(1.0, sp["flops"] / tile_flops) if tile_flops > 0 else 1.0
         roofline = {"kernel": "k_oz_update (tcgen05.mma kind::i8, 36 digit-plane products per FP64 product, accumulators in TMEM)",
-                    "bound": "tensor", "achieved": round(tops, 1), "peak": round(int8_peak, 1), "unit": "TOP/s (int8)",
-                    "frac": round(tops / int8_peak, 4), "traffic": traffic_oz,
+                    "bound": "tensor", "achieved": round(tops, 1), "peak": round(int8_burst, 1), "unit": "TOP/s (int8)",
+                    "frac": round(tops / int8_burst, 4), "traffic": traffic_of("k_oz_update_traffic.json"),
+                    "frac_vs_sustained": round(tops / int8_sust, 4), "peak_sustained": round(int8_sust, 1),
+                    "frac_structural": round(tops * structural_share / int8_burst, 4),
+                    "structural_share_of_tile_flops": round(structural_share, 4),
                     "peak_source": f"2 x dense bf16 {peak_src} (no int8 figure in MEASURED_PEAKS.json; int8 dense = 2 x bf16 dense on B200)",
                     "fp64_equivalent_tflops": round(sp["flops_update_oz"] / (ms_oz * 1e-3) / 1e12, 2),
                     "fp64_dgemm_tflops_measured": round(dgemm_tf, 2),
                     "launches_per_step": int(n_oz), "avg_launch_ms": round(ms_oz / n_oz, 4),
                     "algorithmic_flops_per_step": sp["flops_update_oz"], "tasks_per_step": sp["oz_tasks"],
-                    "share_of_update_ms": round(ms_oz / max(1e-9, sp["ms_assemble"] + sp["ms_factor"]), 3),
+                    "share_of_update_ms": round(ms_oz / ms_fac, 3),
                     "note": "CUDA-event bracket around every launch of the class, kernels serialised (profiling mode)"}
     else:
         roofline = roofline_dmma
@@ -307,37 +397,50 @@ def gpu_arm(args):
     nnz_big = float(np.sum(csum[sym["sn_first"][big_sn + 1]] - csum[sym["sn_first"][big_sn]]))
     ms_big = cls["fwd_big"][0] + cls["bwd_big"][0]
     ach_big = 16.0 * nnz_big / (ms_big * 1e-3) / 1e9 if ms_big > 0 else None
+    whole = {"ms": round(ms_tri, 4), "algorithmic_bytes": 16.0 * sp["nnzL"],
+             "achieved": round(16.0 * sp["nnzL"] / (ms_tri * 1e-3) / 1e9, 1) if ms_tri > 0 else None,
+             "frac": round(16.0 * sp["nnzL"] / (ms_tri * 1e-3) / 1e9 / peaks["hbm_gbs"], 4) if ms_tri > 0 else None,
+             "note": "all sweep kernels of one solve (small / medium / below / big), CUDA-event brackets per launch"}
     roofline_solve = {"kernel": "k_fwd_big + k_bwd_big (dense sweeps over the big supernodes, one rhs)", "bound": "hbm",
                       "achieved": round(ach_big, 1) if ach_big else None, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                       "frac": round(ach_big / peaks["hbm_gbs"], 4) if ach_big else None,
                       "algorithmic_bytes": 16.0 * nnz_big, "ms": round(ms_big, 4), "launches_per_solve": int(cls["fwd_big"][1] + cls["bwd_big"][1]),
                       "streamed_tile_bytes": (bp["n_ftiles"] + bp["n_btiles"]) * 128 * 128 * 8,
                       "share_of_L": round(nnz_big / max(1.0, float(sp["nnzL"])), 4),
-                      "whole_sweep": {"ms": round(ms_tri, 4), "algorithmic_bytes": 16.0 * sp["nnzL"],
-                                      "achieved": round(16.0 * sp["nnzL"] / (ms_tri * 1e-3) / 1e9, 1) if ms_tri > 0 else None,
-                                      "frac": round(16.0 * sp["nnzL"] / (ms_tri * 1e-3) / 1e9 / peaks["hbm_gbs"], 4) if ms_tri > 0 else None,
-                                      "note": "all sweep kernels of one solve (small / medium / below / big), CUDA-event brackets per launch"},
-                      "peak_source": peak_src}
+                      "whole_sweep": whole, "peak_source": peak_src}
     phases = {k: {"ms": round(v[0], 4), "launches": int(v[1])} for k, v in cls.items()}
+    cfg_out = {"workload": workload_name(lp, sysname),
+               "parallelism": "replicas only (this config's elimination tree does not shard)" if world > 1 else "single GPU",
+               "l2": f"inputs larger than L2: factor panels {sp['nnzL_stored'] * 8 / 1e6:.0f} MB streamed every step (L2 126 MB); no explicit flush",
+               "solves_per_step": round(nsolve, 3), "nnzL": sp["nnzL"], "factor_flops": sp["flops"], "nsuper": sp["nsuper"],
+               "levels": sp["nlevels"], "setup_s": round(t_setup, 2), "bytes_device": sp["bytes_device"]}
     out = {
         "metric": METRIC, "value": round(world * K / (ms_total * 1e-3), 4), "unit": UNIT, "n_gpus": world,
         "steps": K, "warmup": W, "ms_per_step": round(ms_total / K, 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(lp, sysname, nsolve),
-                   "parallelism": "replicas only (this config's elimination tree does not shard)" if world > 1 else "single GPU",
-                   "l2": f"inputs larger than L2: factor panels {sp['nnzL_stored'] * 8 / 1e6:.0f} MB streamed every step (L2 126 MB); no explicit flush",
-                   "nnzL": sp["nnzL"], "factor_flops": sp["flops"], "nsuper": sp["nsuper"], "levels": sp["nlevels"],
-                   "setup_s": round(t_setup, 2), "ipm_status_after": h.status, "ipm_iters_run": h.niter},
+        "config": cfg_out, "steps_real": int(k_real),
+        "steps_note": (None if k_real >= K else f"the IPM converged after {len(recs)} iterations: the {K} timed steps cycle over the "
+                       f"{k_real} real post-warm-up iterations"),
         "clocks": clocks,
         "e2e": {"value": round(world * K / e2e_time, 4), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": round(e2e_time * 1e3 / K, 4)},
         "gpu_launches": launches,
         "update_ms_host_api": round(float(np.mean([r["t_update"] for r in timed])) * 1e3, 3),
         "solve_ms_host_api": round(float(np.sum([r["t_solve"] for r in timed]) / np.sum([len(r["rhs"]) for r in timed])) * 1e3, 3),
+        "ipm": ipm,
         "roofline": roofline, "roofline_dmma": roofline_dmma, "roofline_solve": roofline_solve, "phases_one_step": phases,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_sample(pkg, lp, sysname, recs[W])
+        del dev_recs, cache
+        kkt.close()
+        torch.cuda.empty_cache()
+        cached = read_cpu_cache(cfg)
+        if cached is not None:
+            out["cpu_baseline"] = dict(cached["cpu_baseline"], source="measured by `bench.py --impl reference` on this box "
+                                       f"{(time.time() - cached['when']) / 60:.0f} min earlier (cached in {cache_path(cfg)})")
+            out["objective_parity"] = objective_parity(ipm, cached.get("ipm"))
+        else:
+            out["cpu_baseline"] = cpu_sample(pkg, lp, sysname, win[W], cfg)
     if dist:
         dist.barrier()
         dist.destroy_process_group()
@@ -345,65 +448,79 @@ def gpu_arm(args):
         print(json.dumps(out), flush=True)
 
 
-def sharded_arm(args, pkg, lp, sysname, sy, dist, rank, world, local):
-    """BASELINE configs[3]: block-angular LP, elimination-tree subtrees sharded across the ranks, NCCL all-reduce of
-    the separator front (tulip.jl_b200/parallel.py).  Every rank runs the same IPM (SPMD); timing = sum of the
-    KKT calls of the timed iterations through the host API, max over ranks.  Strong scaling: the job is fixed."""
+def sharded_arm(args, cfg, pkg, lp, sysname, sy, dist, rank, world, local):
+    """BASELINE configs[3]: block-angular LP, elimination-tree subtrees sharded across the ranks + reduce of the separator
+    front (tulip.jl_b200/parallel.py).  Every rank runs the same IPM (SPMD); timing = sum of the KKT calls of the timed
+    iterations through the host API, max over ranks.  Strong scaling: the job is fixed; rank 0 first times the same
+    workload on one GPU so that the line carries its own N = 1 figure."""
     import torch
     from tulip_jl_b200 import parallel
     K, W = args.steps, args.warmup
+    m, n = lp.A.shape
+    dev = torch.device(f"cuda:{local}")
+    limit = max(args.ipm_limit, W + K) if args.ipm_limit > 0 else W + K
+    n1 = None
+    if rank == 0 and not args.no_n1:
+        k1 = pkg.setup(lp.A, sy, pkg.Backend(device=local))
+        h1, recs1 = record_hsd(pkg, lp, k1, limit)
+        win1, kr1 = timed_window(recs1, W, K)
+        t1 = sum(r["t_update"] + r["t_solve"] for r in win1[W:W + K])
+        n1 = {"value": round(K / t1, 4), "unit": UNIT, "ms_per_step": round(t1 * 1e3 / K, 4), "steps_real": int(kr1),
+              "update_ms_host_api": round(float(np.mean([r["t_update"] for r in win1[W:W + K]])) * 1e3, 3),
+              "solve_ms_host_api": round(float(np.sum([r["t_solve"] for r in win1[W:W + K]]) / np.sum([len(r["rhs"]) for r in win1[W:W + K]])) * 1e3, 3),
+              "ipm": ipm_summary(h1), "note": "same workload, same host API, one GPU (rank 0), timed in this run before the sharded solver"}
+        k1.close()
+        del k1, recs1, win1
+        torch.cuda.empty_cache()
+    dist.barrier()
     t0 = time.time()
     kkt = parallel.DistB200KKT(lp.A, sy, pkg.Backend(device=local))
     t_setup = time.time() - t0
     sampler = ClockSampler(local)
     dist.barrier(); torch.cuda.synchronize()
     sampler.start()
-    h, recs = record_hsd(pkg, lp, kkt, W + K)
+    h, recs = record_hsd(pkg, lp, kkt, limit)
     torch.cuda.synchronize(); dist.barrier()
     clocks = sampler.stop()
-    base = len(recs)
-    if base < W + 1:
-        raise SystemExit("IPM terminated during warm-up; lower --warmup")
-    timed = recs[W:min(base, W + K)]
-    k_done = len(timed)
-    t = torch.tensor([sum(r["t_update"] + r["t_solve"] for r in timed)], dtype=torch.float64, device=f"cuda:{local}")
+    win, k_real = timed_window(recs, W, K)
+    timed = win[W:W + K]
+    t = torch.tensor([sum(r["t_update"] + r["t_solve"] for r in timed)], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     tot = float(t[0])
     nsolve = float(np.mean([len(r["rhs"]) for r in timed]))
     st = kkt.stats()
-    owner, off, cnt = kkt.dist_info()
-    m, n = lp.A.shape
-    val = k_done / tot
-    out = {"metric": METRIC, "value": round(val, 4), "unit": UNIT, "n_gpus": world, "steps": k_done, "warmup": W,
-           "ms_per_step": round(tot * 1e3 / k_done, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+    comm = kkt.comm_profile() if hasattr(kkt, "comm_profile") else None
+    val = K / tot
+    out = {"metric": METRIC, "value": round(val, 4), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+           "ms_per_step": round(tot * 1e3 / K, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic",
-           "config": {"workload": workload_name(lp, sysname, nsolve),
-                      "parallelism": f"etree subtrees sharded over {world} ranks + NCCL all-reduce of the separator panels "
-                                     f"({cnt * 8 / 1e6:.2f} MB per update!, {2 * 8 * st['order'] / 1e6:.2f} MB per solve!)",
+           "config": {"workload": workload_name(lp, sysname),
+                      "parallelism": f"elimination-tree subtrees sharded over {world} ranks, separator part replicated; "
+                                     + (kkt.describe() if hasattr(kkt, "describe") else "NCCL all-reduce between the phases"),
                       "l2": "timed through the host-pointer API (H2D/D2H inside); factor panels exceed L2",
-                      "nnzL": st["nnzL"], "factor_flops": st["flops"], "setup_s": round(t_setup, 2),
-                      "ipm_status_after": h.status, "ipm_iters_run": h.niter},
-           "clocks": clocks,
+                      "solves_per_step": round(nsolve, 3), "nnzL": st["nnzL"], "factor_flops": st["flops"], "setup_s": round(t_setup, 2),
+                      "bytes_device": st["bytes_device"]},
+           "steps_real": int(k_real), "clocks": clocks, "comm_nranks_seen": [world],
            "e2e": {"value": round(val, 4), "unit": UNIT, "h2d_bytes_per_step": int((2 * n + m) * 8 + nsolve * (n + m) * 8),
-                   "d2h_bytes_per_step": int(4 + nsolve * (n + m) * 8), "ms_per_step": round(tot * 1e3 / k_done, 4)},
-           "gpu_launches": int(k_done * (st["launches_update"] + nsolve * st["launches_solve"])),
+                   "d2h_bytes_per_step": int(4 + nsolve * (n + m) * 8), "ms_per_step": round(tot * 1e3 / K, 4)},
+           "gpu_launches": int(K * (st["launches_update"] + nsolve * st["launches_solve"])),
+           "ipm": ipm_summary(h), "n1_same_workload": n1, "comm": comm,
            "roofline": {"bound": "tensor", "achieved": None, "peak": None, "unit": "TFLOP/s", "frac": None, "traffic": None,
                         "note": "per-kernel roofline is reported by the single-GPU run (--gpus 1)"},
            "update_ms_host_api": round(float(np.mean([r["t_update"] for r in timed])) * 1e3, 3),
            "solve_ms_host_api": round(float(np.sum([r["t_solve"] for r in timed]) / np.sum([len(r["rhs"]) for r in timed])) * 1e3, 3)}
+    if n1 is not None:
+        out["strong_speedup_vs_n1"] = round(val / n1["value"], 3)
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:
         print(json.dumps(out), flush=True)
 
 
-EXTRAPOLATE_ABOVE_FLOPS = 5e12     # one CPU factorisation beyond this does not fit a bounded sample
-
-
-def cpu_sample_extrapolated(st, nsolve):
-    """Bounded CPU sample for a dense-dominated config whose CPU factorisation takes minutes to hours (config T:
-    SURVEY 8d option A): time the two dense kernels that carry > 99 % of the CPU port's work on this workload -- LAPACK
-    dpotrf and the triangular solves, SciPy's OpenBLAS, all host cores -- on an n0 x n0 block, and scale by the
+def cpu_sample_extrapolated(st, nsolve, why):
+    """Fallback CPU sample for a dense-dominated config whose CPU factorisation takes minutes (config T) when the real
+    CPU arm has not run on this box: time the two dense kernels that carry > 99 % of the CPU port's work on this workload --
+    LAPACK dpotrf and the triangular solves, SciPy's OpenBLAS, all host cores -- on an n0 x n0 block, and scale by the
     factorisation's flop count sum_j c_j^2 and the solves' 16 nnz(L) bytes.  Labelled as an extrapolation."""
     import scipy.linalg as sla
     cores = os.cpu_count() or 1
@@ -426,23 +543,25 @@ def cpu_sample_extrapolated(st, nsolve):
     bw = 16.0 * (n0 * (n0 + 1) / 2) / t_s           # algorithmic bytes/s of one forward+backward solve
     t_iter = st["flops"] / rate + nsolve * 16.0 * st["nnzL"] / bw
     return {"value": round(1.0 / t_iter, 6), "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"EXTRAPOLATED (a full CPU factorisation of this config takes ~{st['flops'] / rate / 60:.0f} min): dense dpotrf "
-                      f"{n0}^2 in {t_f:.1f} s = {rate / 1e9:.0f} GF/s (c_j^2 convention) and forward+backward solve at {bw / 1e9:.1f} GB/s, "
-                      f"scaled to sum c_j^2 = {st['flops']:.3e} flops + {nsolve:.2f} solves x 16 nnz(L) = {16.0 * st['nnzL'] / 1e9:.1f} GB",
+            "sample": f"EXTRAPOLATED ({why}): dense dpotrf {n0}^2 in {t_f:.1f} s = {rate / 1e9:.0f} GF/s (c_j^2 convention) and "
+                      f"forward+backward solve at {bw / 1e9:.1f} GB/s, scaled to sum c_j^2 = {st['flops']:.3e} flops + {nsolve:.2f} solves "
+                      f"x 16 nnz(L) = {16.0 * st['nnzL'] / 1e9:.1f} GB",
             "label": "CPU port kernels (SciPy-OpenBLAS dpotrf / dtrsv, all host cores) -- NOT Tulip/CHOLMOD; not run to completion"}
 
 
-def cpu_sample(pkg, lp, sysname, rec):
+def cpu_sample(pkg, lp, sysname, rec, cfg=""):
     """oracle CPU port on a bounded sample: ONE recorded IPM iteration (1 update! + its solves)."""
+    sysname = CPU_SYSTEM.get(cfg, sysname)
     from oracle import cpu_kkt
     A = lp.A
     m, n = A.shape
     sy = pkg.K1() if sysname == "K1" else pkg.K2()
-    an = pkg.setup(A, sy, pkg.Backend(analyze_only=True))
+    an = pkg.setup(A, sy, pkg.Backend(analyze_only=True, dense_col_threshold=-1))
     cores = os.cpu_count() or 1
     st = an.stats()
-    if st["flops"] > EXTRAPOLATE_ABOVE_FLOPS:
-        return cpu_sample_extrapolated(st, float(len(rec["rhs"])))
+    if st["flops"] > ONE_ITER_ABOVE_FLOPS:
+        return cpu_sample_extrapolated(st, float(len(rec["rhs"])), "one CPU factorisation of this config takes minutes; run "
+                                       "`bench.py --impl reference` first on the same box for the measured figure")
     ck = cpu_kkt.CpuSupernodalKKT(A, sysname, nthreads=cores, symbolic_from=an)
     t0 = time.perf_counter()
     ck.update(rec["theta"], rec["regP"], rec["regD"])
@@ -452,7 +571,7 @@ def cpu_sample(pkg, lp, sysname, rec):
     dt = time.perf_counter() - t0
     return {"value": round(1.0 / dt, 5), "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"1 recorded HSD iteration of the same workload (1 update! + {len(rec['rhs'])} solve!), {dt:.2f} s",
-            "label": "CPU port: SciPy SpGEMM assemble + own left-looking supernodal Cholesky on SciPy-OpenBLAS -- NOT Tulip/CHOLMOD"}
+            "label": CPU_LABEL + (f"; CPU system {sysname}" if cfg in CPU_SYSTEM else "")}
 
 
 def reference_arm(args):
@@ -460,7 +579,12 @@ def reference_arm(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    pkg, lp, sysname = build_lp(args.config)
+    cfg = args.config
+    if cfg == "auto":
+        cfg = "T" if world == 1 else "4"
+    pkg, lp, sysname = build_lp(cfg)
+    gpu_sysname = sysname
+    sysname = CPU_SYSTEM.get(cfg, sysname)
     from oracle import cpu_kkt, hsd_ref
     # the reference runs its own vector work with BLAS threads = 1 (model.jl:73); the factorisation's BLAS
     # (SciPy's OpenBLAS, a separate library instance) gets every core below.
@@ -468,20 +592,30 @@ def reference_arm(args):
     threadpool_limits(limits=1, user_api="blas")
     A = lp.A
     sy = pkg.K1() if sysname == "K1" else pkg.K2()
-    an = pkg.setup(A, sy, pkg.Backend(analyze_only=True))       # integer analysis only, no device
+    an = pkg.setup(A, sy, pkg.Backend(analyze_only=True, dense_col_threshold=-1))       # integer analysis only, no device
     cores = os.cpu_count() or 1
     st = an.stats()
-    if st["flops"] > EXTRAPOLATE_ABOVE_FLOPS:
-        nsolve = 5.0
-        cb = cpu_sample_extrapolated(st, nsolve)
-        print(json.dumps({"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": world,
-                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 / cb["value"], 1),
-                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                          "config": {"workload": workload_name(lp, sysname, nsolve)}, "cpu_baseline": cb,
-                          "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
-        return
-    ck = cpu_kkt.CpuSupernodalKKT(A, sysname, nthreads=cores, symbolic_from=an)
     K, W = args.steps, args.warmup
+    one_iter = st["flops"] > ONE_ITER_ABOVE_FLOPS
+    base = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": world, "higher_is_better": True,
+            "scaling": "strong" if (world > 1 and cfg.startswith("4")) else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic"}
+    if one_iter:
+        # panels + the largest descendant-update buffer of the left-looking factorisation (oracle/cpu_supernodal.c)
+        need = 8.0 * (st["nnzL_stored"] + float(st["max_nrow"]) ** 2) * 1.05
+        try:
+            import psutil
+            avail = float(psutil.virtual_memory().available)
+        except Exception:
+            avail = float("inf")
+        if avail < need:
+            cb = cpu_sample_extrapolated(st, 5.0, f"host RAM {avail / 1e9:.0f} GB < {need / 1e9:.0f} GB needed by the CPU port for this config")
+            out = dict(base, value=cb["value"], steps=0, warmup=0, ms_per_step=round(1e3 / cb["value"], 1),
+                       config={"workload": workload_name(lp, gpu_sysname), "solves_per_step": 5.0}, cpu_baseline=cb,
+                       e2e={"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+            print(json.dumps(out), flush=True)
+            return
+        K, W = 1, 0
+    ck = cpu_kkt.CpuSupernodalKKT(A, sysname, nthreads=cores, symbolic_from=an)
     marks = []
 
     class T:
@@ -492,35 +626,45 @@ def reference_arm(args):
             ck.solve(*a)
 
     dat = hsd_ref.IPMData(A, lp.b, True, lp.c, 0.0, lp.l, lp.u)
-    hs = hsd_ref.HSDRef(dat, T(), hsd_ref.IPMOptions(IterationsLimit=W + K))
+    limit = 1 if one_iter else (max(args.ipm_limit, W + K) if args.ipm_limit > 0 else W + K)
+    hs = hsd_ref.HSDRef(dat, T(), hsd_ref.IPMOptions(IterationsLimit=limit))
     hs.optimize(callback=lambda s: marks.append((s.t_factor + s.t_solve, s.n_solve)))
     if len(marks) <= W:
         raise SystemExit("reference arm: IPM ended during warm-up")
     t_w, ns_w = marks[W - 1] if W > 0 else (0.0, 0)
-    t_e, ns_e = marks[-1]
-    k_done = len(marks) - W
+    hi = min(len(marks), W + K)
+    t_e, ns_e = marks[hi - 1]
+    k_done = hi - W
     dt = t_e - t_w
     val = k_done / dt
     nsolve = (ns_e - ns_w) / k_done
-    out = {"impl": "reference", "metric": METRIC, "value": round(val, 5), "unit": UNIT, "n_gpus": world,
-           "steps": k_done, "warmup": W, "ms_per_step": round(dt * 1e3 / k_done, 3), "higher_is_better": True,
-           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": workload_name(lp, sysname, nsolve)},
-           "cpu_baseline": {"value": round(val, 5), "unit": UNIT, "cores": cores, "kind": "port",
-                            "sample": f"{k_done} HSD iterations (after {W} warm-up) of the same workload, {dt:.1f} s of KKT time",
-                            "label": "CPU port: SciPy SpGEMM assemble + own left-looking supernodal Cholesky on SciPy-OpenBLAS -- NOT Tulip/CHOLMOD (no Julia/SuiteSparse in the image)"},
-           "e2e": {"value": round(val, 5), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    ipm = ipm_summary(hs)
+    cb = {"value": round(val, 6), "unit": UNIT, "cores": cores, "kind": "port",
+          "sample": (f"ONE real HSD iteration of the same workload from the reference's start point (1 update! + {ns_e - ns_w} solve!), "
+                     f"{dt:.1f} s of KKT time; not extrapolated" if one_iter else
+                     f"{k_done} HSD iterations (after {W} warm-up) of the same workload, {dt:.3g} s of KKT time"),
+          "label": CPU_LABEL + (f"; CPU system {sysname} (Tulip's default; the reference's K1 would form a dense A D A' here)" if cfg in CPU_SYSTEM else "")}
+    out = dict(base, value=round(val, 6), steps=k_done, warmup=W, ms_per_step=round(dt * 1e3 / k_done, 3),
+               config={"workload": workload_name(lp, gpu_sysname), "solves_per_step": round(nsolve, 3),
+                       "cpu_system": sysname}, cpu_baseline=cb, ipm=ipm,
+               e2e={"value": round(val, 6), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+    try:
+        json.dump({"host": socket.gethostname(), "when": time.time(), "cpu_baseline": cb, "ipm": ipm}, open(cache_path(cfg), "w"))
+    except Exception as e:          # pragma: no cover
+        log(f"could not cache the CPU arm's result: {e}")
     print(json.dumps(out), flush=True)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="2", help="2 (default, BASELINE configs[1]) | 3 | T | mini")
+    ap.add_argument("--config", default="auto", help="auto (T at N=1, 4 sharded at N>1) | T | 2 | 3 | 4 | 5 | mini | 3mini | 4mini | 5mini | Tmini")
+    ap.add_argument("--ipm-limit", type=int, default=100, help="IPM IterationsLimit (reference default 100); 0 = stop after warmup+steps iterations")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-n1", action="store_true", help="sharded run: skip the single-GPU timing of the same workload on rank 0")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         log("note: timing rules ask for >= 3 warm-up steps")

@@ -115,6 +115,13 @@ int tlpb200_solve(tlpb200_solver* s, double* dx, double* dy, const double* xi_p,
 int tlpb200_solve_dev(tlpb200_solver* s, double* d_dx, double* d_dy, const double* d_xi_p, const double* d_xi_d,
                       int32_t nrhs, int64_t ldx, int64_t ldy);
 
+/* result of the solve_dev calls enqueued so far: synchronises; TLPB200_INTERNAL if a sweep kernel's bounded hand-over wait ran
+ * out (results invalid).  tlpb200_solve itself performs this check before returning. */
+int tlpb200_solve_status(tlpb200_solver* s);
+
+/* test hook: raise the device-side "sweep hand-over timed out" flag as a kernel would (the next solve must report it) */
+int tlpb200_debug_raise_timeout(tlpb200_solver* s);
+
 /* stream the _dev calls enqueue on (a cudaStream_t); default: a stream owned by the solver */
 int tlpb200_set_stream(tlpb200_solver* s, void* cuda_stream);
 int tlpb200_synchronize(tlpb200_solver* s);

@@ -115,16 +115,24 @@ def test_solve_parity_vs_oracle(cfg, sysname):
         assert rp <= max(10 * rp0, SQRT_EPS * scale) and rd <= max(10 * rd0, SQRT_EPS * scale)
         ex = np.abs(dx - dx0).max() / max(np.abs(dx0).max(), 1e-300)
         ey = np.abs(dy - dy0).max() / max(np.abs(dy0).max(), 1e-300)
-        # yardstick for ill-conditioned data: the spread between two CPU restatements of the SAME
-        # reference math (sparse SuperLU path vs dense LAPACK/LDL' path).  1e-8 (north_star) where the
-        # problem allows it, otherwise within 100x of the distance between the two oracles.
-        o2 = (kkt_ref.SparseK1 if sysname == "K1" else kkt_ref.SparseK2)(A, dense_below=0 if o._dense else 10 ** 9)
-        o2.update(theta, regP, regD)
-        dx2 = np.zeros(n); dy2 = np.zeros(m)
-        o2.solve(dx2, dy2, xi_p, xi_d)
-        sx = np.abs(dx2 - dx0).max() / max(np.abs(dx0).max(), 1e-300)
-        sy = np.abs(dy2 - dy0).max() / max(np.abs(dy0).max(), 1e-300)
-        assert ex <= max(1e-8, 100 * sx) and ey <= max(1e-8, 100 * sy), (ex, ey, sx, sy)
+        # The bar is 1e-8 (north_star).  Two backward-stable factorisations of the same matrix can only agree to
+        # ~cond(K) * u in the forward error, so a case whose condition number makes 1e-8 unreachable is held to
+        # 10 * cond_2(K) * u instead (computed exactly on the dense matrix: these are the mini configs) and is listed by
+        # name with its condition number in ILL_CONDITIONED_CASES (printed with -rP / on failure).  No floating yardstick.
+        kappa = float(np.linalg.cond(_kkt_matrix(A, sysname, theta, regP, regD)))
+        tol = 1e-8
+        if 10 * kappa * np.finfo(float).eps > tol:
+            tol = 10 * kappa * np.finfo(float).eps
+            ILL_CONDITIONED_CASES[(str(cfg), sysname, spread, reg)] = (kappa, tol, max(ex, ey))
+            print(f"ill-conditioned case cfg{cfg}-mini {sysname} spread={spread} reg={reg}: cond_2(K)={kappa:.3e}, "
+                  f"bar {tol:.2e}, measured {max(ex, ey):.2e}")
+        assert tol <= 1e-4, ("condition number beyond what the test is meant to cover", kappa)
+        assert ex <= tol and ey <= tol, (ex, ey, kappa, tol)
+
+
+# (config, system, theta spread, regularisation) -> (cond_2(K), bar used, measured error) for the per-call cases above
+# whose conditioning makes a 1e-8 forward-error agreement between two correct factorisations impossible
+ILL_CONDITIONED_CASES = {}
 
 
 DENSE_SOLVE_CASES = [
@@ -377,3 +385,90 @@ def test_dense_columns_full_size():
     rp, rd = kkt_ref.kkt_residuals(A, theta, regP, regD, dx, dy, xi_p, xi_d)
     scale = max(1.0, np.abs(dx).max(), np.abs(dy).max())
     assert rp <= SQRT_EPS * scale and rd <= SQRT_EPS * scale
+
+
+# ---- parity at BASELINE sizes against the independent CPU floating point (oracle/cpu_kkt.py) -----------------------
+def _ipm_like_inputs(lp, which, rng):
+    """(theta_inv, regP, regD): 'start' = what the first update! of the reference sees (HSD.jl:238-247 start point,
+    step.jl:24-31: theta_inv in {0,1,2}, regP = regD = 0.1), 'mid' = a mid-run iterate (theta spread e^+-3, reg 1e-5)."""
+    m, n = lp.A.shape
+    if which == "start":
+        theta = np.isfinite(lp.l).astype(float) + np.isfinite(lp.u).astype(float)
+        return theta, np.full(n, 0.1), np.full(m, 0.1)
+    return np.exp(rng.uniform(-3, 3, n)), np.full(n, 1e-5), np.full(m, 1e-5)
+
+
+@pytest.mark.parametrize("cfg,sysname", [(2, "K1"), (3, "K2"), (4, "K1")])
+@pytest.mark.parametrize("which", ["start", "mid"])
+def test_full_size_parity_vs_cpu_port(cfg, sysname, which):
+    """update!/solve! at BASELINE size (tcgen05 path on where the plan uses it) against oracle/cpu_kkt.CpuSupernodalKKT --
+    independent floating point (OpenBLAS left-looking supernodal factorisation) -- to 1e-8 relative, same inputs."""
+    import os
+    from oracle import cpu_kkt
+    lp = lpgen.config(cfg)
+    A = lp.A
+    m, n = A.shape
+    rng = np.random.default_rng(21)
+    theta, regP, regD = _ipm_like_inputs(lp, which, rng)
+    k = pkg.setup(A, SYSTEMS[sysname](), pkg.Backend())
+    if cfg == 2:
+        assert k.stats()["oz_tasks"] > 0, "cfg2 is expected to run its root supernode on the tcgen05 path"
+    an = pkg.setup(A, SYSTEMS[sysname](), pkg.Backend(analyze_only=True))
+    ck = cpu_kkt.CpuSupernodalKKT(A, sysname, nthreads=os.cpu_count(), symbolic_from=an)
+    k.update(theta, regP, regD)
+    ck.update(theta, regP, regD)
+    for _ in range(2):
+        xi_p = rng.standard_normal(m); xi_d = rng.standard_normal(n)
+        dx = np.zeros(n); dy = np.zeros(m); dx0 = np.zeros(n); dy0 = np.zeros(m)
+        k.solve(dx, dy, xi_p, xi_d)
+        ck.solve(dx0, dy0, xi_p, xi_d)
+        ex = np.abs(dx - dx0).max() / np.abs(dx0).max()
+        ey = np.abs(dy - dy0).max() / np.abs(dy0).max()
+        assert ex <= 1e-8 and ey <= 1e-8, (cfg, sysname, which, ex, ey)
+        rp, rd = kkt_ref.kkt_residuals(A, theta, regP, regD, dx, dy, xi_p, xi_d)
+        scale = max(1.0, np.abs(dx).max(), np.abs(dy).max())
+        assert rp <= SQRT_EPS * scale and rd <= SQRT_EPS * scale
+
+
+def test_full_size_parity_dense_columns_vs_cpu_k2():
+    """config 5 at BASELINE size: the K1 dense-column Schur path on the device against the CPU port's K2 factorisation of
+    the SAME linear system ("parity vs oracle K2 on the same LP"; a CPU K1 would form a dense A D A')."""
+    import os
+    from oracle import cpu_kkt
+    lp = lpgen.config(5)
+    A = lp.A
+    m, n = A.shape
+    rng = np.random.default_rng(22)
+    k = pkg.setup(A, pkg.K1(), pkg.Backend())
+    assert len(k.dense_cols()) == 8
+    an = pkg.setup(A, pkg.K2(), pkg.Backend(analyze_only=True))
+    ck = cpu_kkt.CpuSupernodalKKT(A, "K2", nthreads=os.cpu_count(), symbolic_from=an)
+    for which in ("start", "mid"):
+        theta, regP, regD = _ipm_like_inputs(lp, which, rng)
+        k.update(theta, regP, regD)
+        ck.update(theta, regP, regD)
+        xi_p = rng.standard_normal(m); xi_d = rng.standard_normal(n)
+        dx = np.zeros(n); dy = np.zeros(m); dx0 = np.zeros(n); dy0 = np.zeros(m)
+        k.solve(dx, dy, xi_p, xi_d)
+        ck.solve(dx0, dy0, xi_p, xi_d)
+        ex = np.abs(dx - dx0).max() / np.abs(dx0).max()
+        ey = np.abs(dy - dy0).max() / np.abs(dy0).max()
+        assert ex <= 1e-8 and ey <= 1e-8, (which, ex, ey)
+
+
+def test_solve_timeout_flag_is_reported_and_cleared():
+    """a sweep-kernel hand-over time-out must surface from solve! itself.  The flag is raised artificially here
+    (tlpb200_debug_raise_timeout): the next solve! returns TLPB200_INTERNAL, the one after works again."""
+    lp = lpgen.config(2, mini=True)
+    A = lp.A
+    m, n = A.shape
+    k = pkg.setup(A, pkg.K1(), pkg.Backend())
+    k.update(np.ones(n), np.ones(n), np.ones(m))
+    dx = np.zeros(n); dy = np.zeros(m)
+    k.solve(dx, dy, np.ones(m), np.ones(n))
+    k.debug_raise_timeout()
+    with pytest.raises(pkg.TlpB200Error):
+        k.solve(dx, dy, np.ones(m), np.ones(n))
+    k.solve(dx, dy, np.ones(m), np.ones(n))
+    rp, rd = kkt_ref.kkt_residuals(A, np.ones(n), np.ones(n), np.ones(m), dx, dy, np.ones(m), np.ones(n))
+    assert rp <= SQRT_EPS and rd <= SQRT_EPS

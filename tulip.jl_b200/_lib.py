@@ -55,7 +55,7 @@ KERNEL_CLASSES = ["assemble", "small_factor", "diag_factor", "trsm", "update", "
 # every symbol include/tlpb200.h declares (tests check that the library exports all of them)
 SYMBOLS = [
     "tlpb200_default_options", "tlpb200_create", "tlpb200_update", "tlpb200_update_dev",
-    "tlpb200_update_status", "tlpb200_solve", "tlpb200_solve_dev", "tlpb200_set_stream",
+    "tlpb200_update_status", "tlpb200_solve", "tlpb200_solve_dev", "tlpb200_solve_status", "tlpb200_debug_raise_timeout", "tlpb200_set_stream",
     "tlpb200_synchronize", "tlpb200_set_profiling", "tlpb200_stats_get", "tlpb200_get_symbolic",
     "tlpb200_get_structure", "tlpb200_debug_assemble", "tlpb200_debug_get_lx", "tlpb200_last_error",
     "tlpb200_backend_name", "tlpb200_linear_system", "tlpb200_destroy",
@@ -88,6 +88,10 @@ def load():
     lib.tlpb200_update_status.argtypes = [p, C.POINTER(C.c_int64)]
     lib.tlpb200_solve.argtypes = [p, dp, dp, dp, dp, C.c_int32, C.c_int64, C.c_int64]
     lib.tlpb200_solve_dev.argtypes = [p, p, p, p, p, C.c_int32, C.c_int64, C.c_int64]
+    lib.tlpb200_solve_status.argtypes = [p]
+    lib.tlpb200_solve_status.restype = C.c_int
+    lib.tlpb200_debug_raise_timeout.argtypes = [p]
+    lib.tlpb200_debug_raise_timeout.restype = C.c_int
     lib.tlpb200_set_stream.argtypes = [p, p]
     lib.tlpb200_synchronize.argtypes = [p]
     lib.tlpb200_set_profiling.argtypes = [p, C.c_int]

@@ -304,9 +304,15 @@ __global__ void __launch_bounds__(32 * SOLVE_SMALL_WARPS) k_bwd_small(DevCtx c, 
 constexpr int SL_THREADS = 512;
 constexpr int SL_CG = SL_THREADS / SBLK;   // 4 column groups of 32
 
-__device__ __forceinline__ void wait_flag(const int32_t* flag) {
+// The spin is bounded: the grid is sized for co-residency, but anything else holding SMs (a second handle, a
+// caller's stream, NCCL) could keep a producer CTA off the device; a wait that runs out reports through info[2]
+// (-> TLPB200_INTERNAL from the solve) instead of hanging the GPU.
+__device__ __forceinline__ void wait_flag(const int32_t* flag, int32_t* info) {
     if (threadIdx.x == 0) {
-        while (ld_acquire(flag) == 0) { }
+        int spins = 0;
+        while (ld_acquire(flag) == 0) {
+            if (++spins > (1 << 22)) { atomicExch(info + 2, 1); break; }
+        }
     }
     __syncthreads();
 }
@@ -348,7 +354,7 @@ __global__ void __launch_bounds__(SL_THREADS, 1) k_fwd_large(DevCtx c, int32_t b
         };
         if (njt > 0) load_tile(0);
         for (int j = 0; j < njt; ++j) {
-            wait_flag(fflag + db + j);
+            wait_flag(fflag + db + j, c.info);
             if (tid < SBLK) xs[tid] = (j * SBLK + tid < nc) ? __ldcg(c.wk + f + j * SBLK + tid) : 0.0;
             __syncthreads();
 #pragma unroll
@@ -440,7 +446,7 @@ __global__ void __launch_bounds__(SL_THREADS, 1) k_bwd_large(DevCtx c, int32_t b
         }
         // later diagonal blocks except the adjacent one: their x has been available for a while
         for (int32_t j = ncb - 1; j > i + 1; --j) {
-            wait_flag(bflag + db + j);
+            wait_flag(bflag + db + j, c.info);
             const int32_t rr = j * SBLK + r;
             if (rr < nc) {
                 const double xr = __ldcg(c.wk + f + rr);
@@ -472,7 +478,7 @@ __global__ void __launch_bounds__(SL_THREADS, 1) k_bwd_large(DevCtx c, int32_t b
             double t[32];
 #pragma unroll
             for (int cc = 0; cc < 32; ++cc) t[cc] = T[(cg * 32 + cc) * SBLK + r];
-            wait_flag(bflag + db + i + 1);
+            wait_flag(bflag + db + i + 1, c.info);
             if (tid < SBLK) xs[tid] = ((i + 1) * SBLK + tid < nc) ? __ldcg(c.wk + f + (i + 1) * SBLK + tid) : 0.0;
             __syncthreads();
             double a1 = 0.0;

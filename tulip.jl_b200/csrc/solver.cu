@@ -533,6 +533,19 @@ void run_update(tlpb200_solver* s) {
     s->n_update++;
 }
 
+// info[2] (hand-over of a triangular sweep timed out) / info[3] (tcgen05 pipeline timed out) are raised by the kernels and
+// reported by the call that observes them; the device flags are cleared so that the handle's state stays well defined.
+int check_kernel_timeouts(tlpb200_solver* s, const char* where) {
+    const int32_t sweep = s->h_info[2], oz = s->h_info[3];
+    if (sweep == 0 && oz == 0) return TLPB200_OK;
+    cudaMemsetAsync(s->ctx.info + 2, 0, 2 * sizeof(int32_t), s->stream);
+    s->h_info[2] = s->h_info[3] = 0;
+    std::string msg = std::string(where) + ": ";
+    if (sweep) msg += "hand-over of a triangular sweep timed out (a block solution was never published; results are invalid)";
+    if (oz) msg += std::string(sweep ? "; " : "") + "tcgen05 update pipeline timed out (mbarrier never completed)";
+    return fail(s, TLPB200_INTERNAL, msg);
+}
+
 int finish_update(tlpb200_solver* s, int64_t* bad_pivot) {
     CK(cudaStreamSynchronize(s->stream));
     if (s->profiling) {
@@ -544,10 +557,7 @@ int finish_update(tlpb200_solver* s, int64_t* bad_pivot) {
         collect_profile(s, true);
     }
     const int32_t info = *s->h_info;
-    if (s->h_info[2] != 0)
-        return fail(s, TLPB200_INTERNAL, "dense-solve hand-over timed out in an earlier solve (exchange slot never published)");
-    if (s->h_info[3] != 0)
-        return fail(s, TLPB200_INTERNAL, "tcgen05 update pipeline timed out (mbarrier never completed)");
+    if (const int rc = check_kernel_timeouts(s, "update!")) return rc;
     s->bad_pivot = (info >= 0 && info < s->sym.N) ? info : -1;
     if (bad_pivot) *bad_pivot = s->bad_pivot;
     if (s->bad_pivot >= 0) {
@@ -1003,7 +1013,9 @@ int tlpb200_solve(tlpb200_solver* s, double* dx, double* dy, const double* xi_p,
             run_solve_internal(s);
             CK(cudaMemcpyAsync(hout, s->d_dx, n * 8, cudaMemcpyDeviceToHost, s->stream));
             CK(cudaMemcpyAsync(hout + n, s->d_dy, m * 8, cudaMemcpyDeviceToHost, s->stream));
+            CK(cudaMemcpyAsync(s->h_info, s->ctx.info, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, s->stream));
             CK(cudaStreamSynchronize(s->stream));
+            if (const int rc = check_kernel_timeouts(s, "solve!")) return rc;
             if (s->profiling) {
                 float a = 0;
                 CK(cudaEventElapsedTime(&a, s->ev[0], s->ev[3]));
@@ -1037,6 +1049,27 @@ int tlpb200_solve_dev(tlpb200_solver* s, double* d_dx, double* d_dy, const doubl
     } catch (const CudaFail& f) {
         return cuda_fail(s, f);
     }
+}
+
+int tlpb200_solve_status(tlpb200_solver* s) {
+    REQUIRE_DEVICE(s);
+    try {
+        CK(cudaSetDevice(s->device));
+        CK(cudaMemcpyAsync(s->h_info, s->ctx.info, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaStreamSynchronize(s->stream));
+        return check_kernel_timeouts(s, "solve! (device-pointer variant)");
+    } catch (const CudaFail& f) {
+        return cuda_fail(s, f);
+    }
+}
+
+int tlpb200_debug_raise_timeout(tlpb200_solver* s) {
+    REQUIRE_DEVICE(s);
+    const int32_t one = 1;
+    cudaError_t e = cudaMemcpyAsync(s->ctx.info + 2, &one, sizeof one, cudaMemcpyHostToDevice, s->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    if (e != cudaSuccess) return cuda_fail(s, CudaFail{e, "tlpb200_debug_raise_timeout"});
+    return TLPB200_OK;
 }
 
 int tlpb200_set_stream(tlpb200_solver* s, void* cuda_stream) {
@@ -1368,7 +1401,9 @@ int tlpb200_solve_end(tlpb200_solver* s, double* dx, double* dy) {
         double* hout = s->h_pin + (n + m);
         CK(cudaMemcpyAsync(hout, s->d_dx, n * 8, cudaMemcpyDeviceToHost, s->stream));
         CK(cudaMemcpyAsync(hout + n, s->d_dy, m * 8, cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaMemcpyAsync(s->h_info, s->ctx.info, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, s->stream));
         CK(cudaStreamSynchronize(s->stream));
+        if (const int rc = check_kernel_timeouts(s, "solve! (sharded)")) return rc;
         std::memcpy(dx, hout, n * 8);
         std::memcpy(dy, hout + n, m * 8);
         s->launches_solve += cnt;

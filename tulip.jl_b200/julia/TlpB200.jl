@@ -92,6 +92,12 @@ linear_system(::B200Solver{K2}) = "Augmented system (K2)"
 setup(A, system::AbstractKKTSystem, b::Backend) = setup(convert(SparseMatrixCSC{Float64,Int}, A), system, b)
 setup(A::SparseMatrixCSC{Float64,Int}, ::K1, b::Backend) = B200Solver{K1}(A, 1, b)
 setup(A::SparseMatrixCSC{Float64,Int}, ::K2, b::Backend) = B200Solver{K2}(A, 2, b)
+# KKTOptions.System defaults to DefaultKKTSystem (KKT.jl:51), "currently equivalent to K2" (KKT.jl:134-141); without this
+# method the generic convert fallback above would call itself for ever on a SparseMatrixCSC{Float64,Int} (ADVICE r1).
+# The Python mirror maps Default to K2 in the same way (kkt.py).
+setup(A::SparseMatrixCSC{Float64,Int}, ::Tulip.KKT.DefaultKKTSystem, b::Backend) = setup(A, K2(), b)
+setup(A::SparseMatrixCSC{Float64,Int}, system::AbstractKKTSystem, ::Backend) =
+    error("TlpB200: unsupported KKT system $(typeof(system)); use K1() or K2()")
 
 function update!(kkt::B200Solver, θ::AbstractVector{Float64}, regP::AbstractVector{Float64}, regD::AbstractVector{Float64})
     m, n = kkt.m, kkt.n

@@ -206,6 +206,17 @@ class B200KKTSolver:
         if rc != _lib.OK:
             _raise(rc, self._h)
 
+    def solve_status(self):
+        """synchronise and raise if a sweep kernel of the solve_dev calls enqueued so far timed out"""
+        rc = _lib.load().tlpb200_solve_status(self._h)
+        if rc != _lib.OK:
+            _raise(rc, self._h)
+
+    def debug_raise_timeout(self):
+        rc = _lib.load().tlpb200_debug_raise_timeout(self._h)
+        if rc != _lib.OK:
+            _raise(rc, self._h)
+
     def synchronize(self):
         rc = _lib.load().tlpb200_synchronize(self._h)
         if rc != _lib.OK:
