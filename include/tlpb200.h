@@ -36,7 +36,8 @@ enum {
     TLPB200_OOM = 2,        /* host or device allocation failed -> Julia OutOfMemoryError (HSD.jl:327) */
     TLPB200_BAD_ARG = 3,    /* dimension / argument error -> Julia DimensionMismatch (spd.jl:26-34) */
     TLPB200_CUDA = 4,       /* CUDA runtime error or no usable device -> ErrorException */
-    TLPB200_INTERNAL = 5
+    TLPB200_INTERNAL = 5,
+    TLPB200_NCCL = 6        /* NCCL error (multi-GPU collectives) -> ErrorException */
 };
 
 enum { TLPB200_K1 = 1, TLPB200_K2 = 2 }; /* src/KKT/systems.jl:32 (K2), :54 (K1) */
@@ -82,7 +83,7 @@ typedef struct tlpb200_stats {
     /* profiling mode: CUDA-event time and launch count per kernel class of the last update!/solve!
      * 0 assemble  1 small_factor  2 diag_factor  3 trsm  4 update  5 rhs+recover
      * 6 fwd_small 7 fwd_large 8 -  9 bwd_large 10 invert_diag 11 bwd_small */
-    double ms_class[TLPB200_NCLASS];   /* ... 12 dense_cols 13 pack_big 14 fwd_big 15 bwd_big 16 oz_slice 17 oz_update */
+    double ms_class[TLPB200_NCLASS];   /* ... 12 dense_cols 13 pack_big 14 fwd_big 15 bwd_big 16 oz_slice 17 oz_update 18 collectives */
     int64_t n_class[TLPB200_NCLASS];
     double flops_update_oz; /* algorithmic flops of one update! done by the tcgen05 int8 tasks (not part of flops_update_ext) */
     int64_t oz_tasks;       /* tcgen05 tasks per update! */
@@ -180,6 +181,19 @@ int tlpb200_solve_begin(tlpb200_solver* s, const double* xi_p, const double* xi_
 int tlpb200_work_vector(tlpb200_solver* s, void** dptr, int64_t* count);
 int tlpb200_solve_mid(tlpb200_solver* s);
 int tlpb200_solve_end(tlpb200_solver* s, double* dx, double* dy);
+
+/* In-library collectives (preferred over the phase API above): after tlpb200_comm_init the ordinary entry points
+ * tlpb200_update / tlpb200_update_dev / tlpb200_solve / tlpb200_solve_dev run the whole sharded sequence -- own subtrees,
+ * NCCL all-reduce of the top panels / of the separator entries of the work vector, replicated top part -- as ONE
+ * stream-ordered (CUDA-graph) sequence on the solver's stream, without host synchronisation between the phases; return
+ * codes are identical on every rank (the status words are all-reduced).  One rank calls tlpb200_comm_unique_id (128 bytes,
+ * an ncclUniqueId), the caller's own plumbing broadcasts it (torch.distributed in tulip.jl_b200/parallel.py), then EVERY
+ * rank calls tlpb200_comm_init (collective).  NCCL is resolved at run time (dlopen of libnccl.so.2). */
+int tlpb200_comm_unique_id(void* out128);
+int tlpb200_comm_init(tlpb200_solver* s, const void* id128);
+/* mean time [ms] of each collective of a sharded update!/solve!, timed alone (`reps` back-to-back calls): [0] top panels,
+ * [1] separator entries, [2] solution vector, [3] status words; bytes[] = their payloads.  Collective call. */
+int tlpb200_comm_profile(tlpb200_solver* s, int32_t reps, float* ms /* 4 */, int64_t* bytes /* 4 */);
 
 /* K1 dense-column path: number and (0-based) indices of the columns kept out of the sparse factor */
 int tlpb200_get_dense_cols(const tlpb200_solver* s, int32_t* count, int64_t* cols /* may be NULL */);

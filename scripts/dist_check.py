@@ -26,7 +26,8 @@ def main():
     rank, world = dist.get_rank(), dist.get_world_size()
     which = sys.argv[1] if len(sys.argv) > 1 else "mini"
     ok = True
-    for sysname in ("K1", "K2"):
+    modes = [m_ for m_ in os.environ.get("TLPB200_DIST_MODES", "library,phases").split(",") if m_]
+    for sysname, mode in [(s_, m_) for s_ in ("K1", "K2") for m_ in modes]:
         lp = lpgen.config(4, mini=(which == "mini"))
         A = lp.A
         m, n = A.shape
@@ -34,7 +35,7 @@ def main():
         theta = np.exp(rng.uniform(-4, 4, n)); regP = np.full(n, 1e-6); regD = np.full(m, 1e-6)
         xi_p = rng.standard_normal(m); xi_d = rng.standard_normal(n)
         sy = pkg.K1() if sysname == "K1" else pkg.K2()
-        k = parallel.DistB200KKT(A, sy, pkg.Backend(device=local))
+        k = parallel.DistB200KKT(A, sy, pkg.Backend(device=local), mode=mode)
         owner, off, cnt = k.dist_info()
         k.update(theta, regP, regD)
         dx = np.zeros(n); dy = np.zeros(m)
@@ -49,7 +50,7 @@ def main():
         tt = torch.tensor(min(t), dtype=torch.float64, device=f"cuda:{local}")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         rp, rd = kkt_ref.kkt_residuals(A, theta, regP, regD, dx, dy, xi_p, xi_d)
-        msg = f"[{sysname}] world={world} m={m} n={n} top={cnt * 8 / 1e6:.2f} MB shards={np.bincount(owner[owner >= 0], minlength=world).tolist()} " \
+        msg = f"[{sysname}/{mode}] world={world} m={m} n={n} top={cnt * 8 / 1e6:.2f} MB shards={np.bincount(owner[owner >= 0], minlength=world).tolist()} " \
               f"update {tt[0].item() * 1e3:.2f} ms solve {tt[1].item() * 1e3:.2f} ms |rp|={rp:.2e} |rd|={rd:.2e}"
         scale = max(1.0, np.abs(dx).max(), np.abs(dy).max())
         good = rp <= 1.5e-8 * scale and rd <= 1.5e-8 * scale
@@ -73,8 +74,12 @@ def main():
             raised = True
         good = good and raised
         k.update(theta, regP, regD)       # still usable
+        if mode == "library":
+            cp = k.comm_profile(20)
+            msg += f" | collectives/update {cp['per_update_ms']:.3f} ms, /solve {cp['per_solve_ms']:.3f} ms"
         if rank == 0:
             print(msg, "posdef-consistent" if raised else "POSDEF-NOT-RAISED", flush=True)
+        k.close()
         ok = ok and good
     flag = torch.tensor([1 if ok else 0], device=f"cuda:{local}")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)

@@ -13,7 +13,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtlpb200.so")
 
-OK, NOT_POSDEF, OOM, BAD_ARG, CUDA, INTERNAL = 0, 1, 2, 3, 4, 5
+OK, NOT_POSDEF, OOM, BAD_ARG, CUDA, INTERNAL, NCCL = 0, 1, 2, 3, 4, 5, 6
 K1, K2 = 1, 2
 
 
@@ -49,13 +49,13 @@ class Stats(C.Structure):
 
 KERNEL_CLASSES = ["assemble", "small_factor", "diag_factor", "trsm", "update", "rhs_recover",
                   "fwd_small", "fwd_large", "update128", "bwd_large", "invert_diag", "bwd_small", "dense_cols",
-                  "pack_big", "fwd_big", "bwd_big", "oz_slice", "oz_update"]
+                  "pack_big", "fwd_big", "bwd_big", "oz_slice", "oz_update", "comm"]
 
 
 # every symbol include/tlpb200.h declares (tests check that the library exports all of them)
 SYMBOLS = [
     "tlpb200_default_options", "tlpb200_create", "tlpb200_update", "tlpb200_update_dev",
-    "tlpb200_update_status", "tlpb200_solve", "tlpb200_solve_dev", "tlpb200_solve_status", "tlpb200_debug_raise_timeout", "tlpb200_set_stream",
+    "tlpb200_update_status", "tlpb200_solve", "tlpb200_solve_dev", "tlpb200_solve_status", "tlpb200_debug_raise_timeout", "tlpb200_comm_unique_id", "tlpb200_comm_init", "tlpb200_comm_profile", "tlpb200_set_stream",
     "tlpb200_synchronize", "tlpb200_set_profiling", "tlpb200_stats_get", "tlpb200_get_symbolic",
     "tlpb200_get_structure", "tlpb200_debug_assemble", "tlpb200_debug_get_lx", "tlpb200_last_error",
     "tlpb200_backend_name", "tlpb200_linear_system", "tlpb200_destroy",
@@ -92,6 +92,12 @@ def load():
     lib.tlpb200_solve_status.restype = C.c_int
     lib.tlpb200_debug_raise_timeout.argtypes = [p]
     lib.tlpb200_debug_raise_timeout.restype = C.c_int
+    lib.tlpb200_comm_unique_id.argtypes = [p]
+    lib.tlpb200_comm_unique_id.restype = C.c_int
+    lib.tlpb200_comm_init.argtypes = [p, p]
+    lib.tlpb200_comm_init.restype = C.c_int
+    lib.tlpb200_comm_profile.argtypes = [p, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_int64)]
+    lib.tlpb200_comm_profile.restype = C.c_int
     lib.tlpb200_set_stream.argtypes = [p, p]
     lib.tlpb200_synchronize.argtypes = [p]
     lib.tlpb200_set_profiling.argtypes = [p, C.c_int]

@@ -604,6 +604,25 @@ __global__ void k_zero_unowned(DevCtx c, const int8_t* __restrict__ keep) {
     if (q < c.N && !keep[q]) c.wk[q] = 0.0;
 }
 
+// multi-GPU: the separator ("top") entries of the work vector, packed for the small all-reduce between the local forward
+// sweeps and the replicated top solve (a 512-vector per solve on config 4), and unpacked afterwards
+__global__ void k_gather_top(const double* __restrict__ wk, const int32_t* __restrict__ cols, int32_t ntop, double* __restrict__ buf) {
+    const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < ntop) buf[i] = wk[cols[i]];
+}
+__global__ void k_scatter_top(double* __restrict__ wk, const int32_t* __restrict__ cols, int32_t ntop, const double* __restrict__ buf) {
+    const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < ntop) wk[cols[i]] = buf[i];
+}
+// multi-GPU: the factorisation status words, arranged so that ONE max-all-reduce makes them identical on every rank
+// (info[0] = smallest bad pivot column -> INT_MAX - info[0]; info[2], info[3] = time-out flags), and back
+__global__ void k_pack_info(const int32_t* __restrict__ info, int32_t* __restrict__ tmp) {
+    if (threadIdx.x == 0) { tmp[0] = 0x7fffffff - info[0]; tmp[1] = info[2]; tmp[2] = info[3]; tmp[3] = 0; }
+}
+__global__ void k_unpack_info(int32_t* __restrict__ info, const int32_t* __restrict__ tmp) {
+    if (threadIdx.x == 0) { info[0] = 0x7fffffff - tmp[0]; info[2] = tmp[1]; info[3] = tmp[2]; }
+}
+
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
@@ -667,6 +686,14 @@ void launch_bwd_large(const DevCtx& c, int32_t begin, int32_t end, int nsm, cuda
 void launch_bwd_below(const DevCtx& c, int32_t begin, int32_t end, cudaStream_t st) {
     if (end > begin) k_bwd_below<<<(unsigned)(end - begin), SL_THREADS, 0, st>>>(c, begin);
 }
+void launch_gather_top(const double* wk, const int32_t* cols, int32_t ntop, double* buf, cudaStream_t st) {
+    if (ntop > 0) k_gather_top<<<(unsigned)((ntop + 255) / 256), 256, 0, st>>>(wk, cols, ntop, buf);
+}
+void launch_scatter_top(double* wk, const int32_t* cols, int32_t ntop, const double* buf, cudaStream_t st) {
+    if (ntop > 0) k_scatter_top<<<(unsigned)((ntop + 255) / 256), 256, 0, st>>>(wk, cols, ntop, buf);
+}
+void launch_pack_info(const int32_t* info, int32_t* tmp, cudaStream_t st) { k_pack_info<<<1, 32, 0, st>>>(info, tmp); }
+void launch_unpack_info(int32_t* info, const int32_t* tmp, cudaStream_t st) { k_unpack_info<<<1, 32, 0, st>>>(info, tmp); }
 void launch_zero_unowned(const DevCtx& c, const int8_t* keep, cudaStream_t st) {
     if (c.N > 0) k_zero_unowned<<<nblk(c.N, 256), 256, 0, st>>>(c, keep);
 }

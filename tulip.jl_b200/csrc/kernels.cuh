@@ -136,6 +136,10 @@ void launch_fwd_big(const DevCtx& c, int32_t begin, int32_t end, int nsm, cudaSt
 void launch_bwd_big(const DevCtx& c, int32_t begin, int32_t end, int nsm, cudaStream_t st);
 cudaError_t dense_solve_static_init();
 
+void launch_gather_top(const double* wk, const int32_t* cols, int32_t ntop, double* buf, cudaStream_t st);
+void launch_scatter_top(double* wk, const int32_t* cols, int32_t ntop, const double* buf, cudaStream_t st);
+void launch_pack_info(const int32_t* info, int32_t* tmp, cudaStream_t st);
+void launch_unpack_info(int32_t* info, const int32_t* tmp, cudaStream_t st);
 void launch_zero_unowned(const DevCtx& c, const int8_t* keep, cudaStream_t st);   // wk[q] = 0 where keep[q] == 0
 void launch_k1_rhs(const DevCtx& c, const DevMat& A, const double* d, const double* xi_p, const double* xi_d,
                    cudaStream_t st);

@@ -4,6 +4,8 @@
 // cholmod.jl:46-60): setup once (spd.jl:5-20 / sqd.jl:5-22), then per IPM iteration one update!
 // (spd.jl:22-50 / sqd.jl:24-55) and 3-6 solve! calls (spd.jl:52-70 / sqd.jl:57-74).
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>   // types and enums only: the library is resolved at run time (dlopen), see NcclApi below
 
 #include <algorithm>
 #include <chrono>
@@ -59,6 +61,14 @@ struct tlpb200_solver {
     std::vector<int32_t> owner;   // [nsuper] rank owning each supernode, -1 = replicated top part
     int64_t top_begin = 0;        // offset of the top panels inside Lx
     int8_t* d_keep = nullptr;     // [N] 1 = this rank contributes wk[q] to the all-reduce
+    // in-library collectives (tlpb200_comm_init): NCCL on the solver's stream, so that a sharded update!/solve! is ONE
+    // stream-ordered (graph-captured) sequence without host synchronisation between its phases
+    ncclComm_t comm = nullptr;
+    int32_t ntop = 0;             // columns of the replicated top (separator) part
+    const int32_t* d_top_cols = nullptr;   // [ntop] their permuted indices
+    double* d_tbuf = nullptr;     // [ntop] packed top entries of wk for the small all-reduce of a solve
+    int32_t* d_info_tmp = nullptr;   // [4] status words arranged for one max-all-reduce
+    bool dist_graph = true;       // TLPB200_DIST_GRAPH=0: launch the sharded sequences without CUDA graphs
     DevMat mat{};
     double *d_theta = nullptr, *d_regP = nullptr, *d_regD = nullptr, *d_d = nullptr;
     double *d_xip = nullptr, *d_xid = nullptr, *d_dx = nullptr, *d_dy = nullptr;
@@ -183,6 +193,57 @@ int cuda_fail(tlpb200_solver* s, const CudaFail& f) {
     cudaGetLastError();
     return fail(s, f.e == cudaErrorMemoryAllocation ? TLPB200_OOM : TLPB200_CUDA, buf);
 }
+
+// NCCL is taken from the process at run time: torch has already loaded its bundled libnccl.so.2 when the Python host
+// mirror drives the library (RTLD_NOLOAD finds that copy); a stand-alone caller gets the system library.  Nothing is
+// linked, so the single-GPU product and the CPU-only tests do not depend on NCCL being installed.
+struct NcclApi {
+    void* h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    ncclResult_t (*GetVersion)(int*) = nullptr;
+    std::string err;
+};
+
+NcclApi& nccl_api() {
+    static NcclApi api;
+    if (api.h || !api.err.empty()) return api;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) { api.err = std::string("libnccl.so.2 not found: ") + (dlerror() ? dlerror() : ""); return api; }
+    api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+    api.CommInitRank = (decltype(api.CommInitRank))dlsym(h, "ncclCommInitRank");
+    api.AllReduce = (decltype(api.AllReduce))dlsym(h, "ncclAllReduce");
+    api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
+    api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
+    api.GetVersion = (decltype(api.GetVersion))dlsym(h, "ncclGetVersion");
+    if (!api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.CommDestroy) { api.err = "libnccl.so.2 lacks the expected symbols"; return api; }
+    api.h = h;
+    return api;
+}
+
+struct NcclFail {
+    ncclResult_t e;
+    const char* what;
+};
+#define NK(call)                                               \
+    do {                                                       \
+        ncclResult_t _e = (call);                              \
+        if (_e != ncclSuccess) throw NcclFail{_e, #call};      \
+    } while (0)
+
+int nccl_fail(tlpb200_solver* s, const NcclFail& f) {
+    char buf[512];
+    const NcclApi& api = nccl_api();
+    snprintf(buf, sizeof buf, "NCCL error %d (%s) in %s", (int)f.e, api.GetErrorString ? api.GetErrorString(f.e) : "?", f.what);
+    return fail(s, TLPB200_NCCL, buf);
+}
+
+inline bool sharded(const tlpb200_solver* s) { return s->nranks > 1; }
 
 // ---- the numeric phases, enqueued on s->stream; `count` accumulates kernel launches -------------
 void enqueue_assemble(tlpb200_solver* s, int64_t& count) {
@@ -473,6 +534,77 @@ void enqueue_solve(tlpb200_solver* s, const double* xip, const double* xid, doub
     enqueue_recover(s, xid, dx, dy, count);
 }
 
+// Sharded (nranks > 1) update!: own subtrees -> all-reduce(sum) of the partial top panels over NVLink -> replicated top
+// part -> one max-all-reduce of the status words (so that PosDefException / time-outs are raised on EVERY rank, step.jl:34-51).
+// Everything is enqueued on the solver's stream: no host synchronisation between the phases.
+void enqueue_update_all(tlpb200_solver* s, int64_t& cnt) {
+    if (!sharded(s)) {
+        enqueue_assemble(s, cnt);
+        enqueue_factor(s, cnt);
+        return;
+    }
+    const NcclApi& api = nccl_api();
+    const int64_t top_cnt = s->sym.lx_size - s->top_begin;
+    s->cur = &s->ctx;
+    enqueue_assemble(s, cnt);
+    // original entries of the replicated top part are contributed by rank 0 only
+    if (s->rank != 0 && top_cnt > 0) CK(cudaMemsetAsync(s->ctx.Lx + s->top_begin, 0, (size_t)top_cnt * 8, s->stream));
+    s->cur = &s->ctxA;
+    enqueue_factor(s, cnt);
+    if (top_cnt > 0) {
+        Scope sc(s, 18);
+        NK(api.AllReduce(s->ctx.Lx + s->top_begin, s->ctx.Lx + s->top_begin, (size_t)top_cnt, ncclFloat64, ncclSum, s->comm, s->stream));
+        cnt++;
+    }
+    CK(cudaMemsetAsync(s->lazy_ctr, 0, (2 * s->plan.levels.size() + 2) * sizeof(int32_t), s->stream));
+    s->cur = &s->ctxB;
+    enqueue_factor(s, cnt);
+    s->cur = &s->ctx;
+    {
+        Scope sc(s, 18);
+        launch_pack_info(s->ctx.info, s->d_info_tmp, s->stream);
+        NK(api.AllReduce(s->d_info_tmp, s->d_info_tmp, 4, ncclInt32, ncclMax, s->comm, s->stream));
+        launch_unpack_info(s->ctx.info, s->d_info_tmp, s->stream);
+        cnt += 3;
+    }
+}
+
+// Sharded solve!: forward sweep on own subtrees -> all-reduce(sum) of the separator entries only (ntop doubles)
+// -> replicated top forward + backward -> backward sweep on own subtrees -> all-reduce of the zero-padded solution (every
+// rank's host IPM needs the whole vector) -> recovery.  One stream-ordered sequence.
+void enqueue_solve_all(tlpb200_solver* s, const double* xip, const double* xid, double* dx, double* dy, int64_t& cnt) {
+    if (!sharded(s)) {
+        enqueue_solve(s, xip, xid, dx, dy, cnt);
+        return;
+    }
+    const NcclApi& api = nccl_api();
+    s->cur = &s->ctx;
+    enqueue_rhs(s, xip, xid, cnt);
+    launch_zero_unowned(s->ctx, s->d_keep, s->stream);
+    s->cur = &s->ctxA;
+    enqueue_fwd(s, cnt);
+    if (s->ntop > 0) {
+        Scope sc(s, 18);
+        launch_gather_top(s->ctx.wk, s->d_top_cols, s->ntop, s->d_tbuf, s->stream);
+        NK(api.AllReduce(s->d_tbuf, s->d_tbuf, (size_t)s->ntop, ncclFloat64, ncclSum, s->comm, s->stream));
+        launch_scatter_top(s->ctx.wk, s->d_top_cols, s->ntop, s->d_tbuf, s->stream);
+        cnt += 3;
+    }
+    s->cur = &s->ctxB;
+    enqueue_fwd(s, cnt);
+    enqueue_bwd(s, cnt);
+    s->cur = &s->ctxA;
+    enqueue_bwd(s, cnt);
+    s->cur = &s->ctx;
+    launch_zero_unowned(s->ctx, s->d_keep, s->stream);
+    {
+        Scope sc(s, 18);
+        NK(api.AllReduce(s->ctx.wk, s->ctx.wk, (size_t)s->sym.N, ncclFloat64, ncclSum, s->comm, s->stream));
+        cnt += 3;
+    }
+    enqueue_recover(s, xid, dx, dy, cnt);
+}
+
 void destroy_graphs(tlpb200_solver* s) {
     if (s->g_update) { cudaGraphExecDestroy(s->g_update); s->g_update = nullptr; }
     if (s->g_solve) { cudaGraphExecDestroy(s->g_solve); s->g_solve = nullptr; }
@@ -484,9 +616,9 @@ void build_graphs(tlpb200_solver* s) {
     int64_t cnt = 0;
     CK(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
     try {
-        enqueue_assemble(s, cnt);
-        enqueue_factor(s, cnt);
+        enqueue_update_all(s, cnt);
     } catch (...) {
+        s->cur = &s->ctx;
         cudaStreamEndCapture(s->stream, &g);
         if (g) cudaGraphDestroy(g);
         throw;
@@ -499,8 +631,9 @@ void build_graphs(tlpb200_solver* s) {
     cnt = 0;
     CK(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
     try {
-        enqueue_solve(s, s->d_xip, s->d_xid, s->d_dx, s->d_dy, cnt);
+        enqueue_solve_all(s, s->d_xip, s->d_xid, s->d_dx, s->d_dy, cnt);
     } catch (...) {
+        s->cur = &s->ctx;
         cudaStreamEndCapture(s->stream, &g);
         if (g) cudaGraphDestroy(g);
         throw;
@@ -512,7 +645,9 @@ void build_graphs(tlpb200_solver* s) {
 }
 
 void run_update(tlpb200_solver* s) {
-    if (s->profiling) {
+    if (sharded(s) && !s->comm) throw std::runtime_error("solver was created with nranks > 1: call tlpb200_comm_init first (or drive the phase API: update_begin / update_end)");
+    const bool graph = s->opt.use_graph && (!sharded(s) || s->dist_graph);
+    if (s->profiling && !sharded(s)) {
         int64_t cnt = 0;
         CK(cudaEventRecord(s->ev[0], s->stream));
         enqueue_assemble(s, cnt);
@@ -520,13 +655,19 @@ void run_update(tlpb200_solver* s) {
         enqueue_factor(s, cnt);
         CK(cudaEventRecord(s->ev[2], s->stream));
         s->launches_update = cnt;
-    } else if (s->opt.use_graph) {
+    } else if (s->profiling) {
+        int64_t cnt = 0;
+        CK(cudaEventRecord(s->ev[0], s->stream));
+        CK(cudaEventRecord(s->ev[1], s->stream));
+        enqueue_update_all(s, cnt);
+        CK(cudaEventRecord(s->ev[2], s->stream));
+        s->launches_update = cnt;
+    } else if (graph) {
         if (!s->g_update) build_graphs(s);
         CK(cudaGraphLaunch(s->g_update, s->stream));
     } else {
         int64_t cnt = 0;
-        enqueue_assemble(s, cnt);
-        enqueue_factor(s, cnt);
+        enqueue_update_all(s, cnt);
         s->launches_update = cnt;
     }
     CK(cudaMemcpyAsync(s->h_info, s->ctx.info, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, s->stream));
@@ -571,18 +712,20 @@ int finish_update(tlpb200_solver* s, int64_t* bad_pivot) {
 
 // solve one right-hand side held in the internal buffers d_xip/d_xid -> d_dx/d_dy
 void run_solve_internal(tlpb200_solver* s) {
+    if (sharded(s) && !s->comm) throw std::runtime_error("solver was created with nranks > 1: call tlpb200_comm_init first (or drive the phase API: solve_begin / solve_mid / solve_end)");
+    const bool graph = s->opt.use_graph && (!sharded(s) || s->dist_graph);
     if (s->profiling) {
         int64_t cnt = 0;
         CK(cudaEventRecord(s->ev[0], s->stream));
-        enqueue_solve(s, s->d_xip, s->d_xid, s->d_dx, s->d_dy, cnt);
+        enqueue_solve_all(s, s->d_xip, s->d_xid, s->d_dx, s->d_dy, cnt);
         CK(cudaEventRecord(s->ev[3], s->stream));
         s->launches_solve = cnt;
-    } else if (s->opt.use_graph) {
+    } else if (graph) {
         if (!s->g_solve) build_graphs(s);
         CK(cudaGraphLaunch(s->g_solve, s->stream));
     } else {
         int64_t cnt = 0;
-        enqueue_solve(s, s->d_xip, s->d_xid, s->d_dx, s->d_dy, cnt);
+        enqueue_solve_all(s, s->d_xip, s->d_xid, s->d_dx, s->d_dy, cnt);
         s->launches_solve = cnt;
     }
     s->n_solve++;
@@ -717,6 +860,15 @@ void setup_device(tlpb200_solver* s) {
         s->ctxA = s->ctx; s->ctxA.skip = upload(s, skipA);
         s->ctxB = s->ctx; s->ctxB.skip = upload(s, skipB);
         s->d_keep = const_cast<int8_t*>(upload(s, keep));
+        std::vector<int32_t> top_cols;
+        for (int32_t sn = 0; sn < S.nsuper; ++sn)
+            if (s->owner[sn] == -1)
+                for (int32_t j = S.sn_first[sn]; j < S.sn_first[sn + 1]; ++j) top_cols.push_back(j);
+        s->ntop = (int32_t)top_cols.size();
+        s->d_top_cols = upload(s, top_cols);
+        s->d_tbuf = dalloc<double>(s, std::max<size_t>(top_cols.size(), 1));
+        s->d_info_tmp = dalloc<int32_t>(s, 4);
+        if (const char* e = getenv("TLPB200_DIST_GRAPH")) s->dist_graph = atoi(e) != 0;
     }
     if (!P.oz_views.empty()) {
         int lo = 0, hi = 0;
@@ -969,6 +1121,12 @@ int tlpb200_update(tlpb200_solver* s, const double* theta_inv, const double* reg
         return rc;
     } catch (const CudaFail& f) {
         return cuda_fail(s, f);
+    } catch (const NcclFail& f) {
+        s->cur = &s->ctx;
+        return nccl_fail(s, f);
+    } catch (const std::exception& e) {
+        s->cur = &s->ctx;
+        return fail(s, TLPB200_INTERNAL, e.what());
     }
 }
 
@@ -983,6 +1141,12 @@ int tlpb200_update_dev(tlpb200_solver* s, const double* d_theta_inv, const doubl
         return TLPB200_OK;
     } catch (const CudaFail& f) {
         return cuda_fail(s, f);
+    } catch (const NcclFail& f) {
+        s->cur = &s->ctx;
+        return nccl_fail(s, f);
+    } catch (const std::exception& e) {
+        s->cur = &s->ctx;
+        return fail(s, TLPB200_INTERNAL, e.what());
     }
 }
 
@@ -992,6 +1156,12 @@ int tlpb200_update_status(tlpb200_solver* s, int64_t* bad_pivot) {
         return finish_update(s, bad_pivot);
     } catch (const CudaFail& f) {
         return cuda_fail(s, f);
+    } catch (const NcclFail& f) {
+        s->cur = &s->ctx;
+        return nccl_fail(s, f);
+    } catch (const std::exception& e) {
+        s->cur = &s->ctx;
+        return fail(s, TLPB200_INTERNAL, e.what());
     }
 }
 
@@ -1028,6 +1198,12 @@ int tlpb200_solve(tlpb200_solver* s, double* dx, double* dy, const double* xi_p,
         return TLPB200_OK;
     } catch (const CudaFail& f) {
         return cuda_fail(s, f);
+    } catch (const NcclFail& f) {
+        s->cur = &s->ctx;
+        return nccl_fail(s, f);
+    } catch (const std::exception& e) {
+        s->cur = &s->ctx;
+        return fail(s, TLPB200_INTERNAL, e.what());
     }
 }
 
@@ -1048,6 +1224,12 @@ int tlpb200_solve_dev(tlpb200_solver* s, double* d_dx, double* d_dy, const doubl
         return TLPB200_OK;
     } catch (const CudaFail& f) {
         return cuda_fail(s, f);
+    } catch (const NcclFail& f) {
+        s->cur = &s->ctx;
+        return nccl_fail(s, f);
+    } catch (const std::exception& e) {
+        s->cur = &s->ctx;
+        return fail(s, TLPB200_INTERNAL, e.what());
     }
 }
 
@@ -1060,6 +1242,12 @@ int tlpb200_solve_status(tlpb200_solver* s) {
         return check_kernel_timeouts(s, "solve! (device-pointer variant)");
     } catch (const CudaFail& f) {
         return cuda_fail(s, f);
+    } catch (const NcclFail& f) {
+        s->cur = &s->ctx;
+        return nccl_fail(s, f);
+    } catch (const std::exception& e) {
+        s->cur = &s->ctx;
+        return fail(s, TLPB200_INTERNAL, e.what());
     }
 }
 
@@ -1157,6 +1345,12 @@ int tlpb200_debug_assemble(tlpb200_solver* s, const double* theta_inv, const dou
         return TLPB200_OK;
     } catch (const CudaFail& f) {
         return cuda_fail(s, f);
+    } catch (const NcclFail& f) {
+        s->cur = &s->ctx;
+        return nccl_fail(s, f);
+    } catch (const std::exception& e) {
+        s->cur = &s->ctx;
+        return fail(s, TLPB200_INTERNAL, e.what());
     }
 }
 
@@ -1170,6 +1364,12 @@ int tlpb200_debug_get_lx(tlpb200_solver* s, double* lx, int64_t* xptr) {
         return TLPB200_OK;
     } catch (const CudaFail& f) {
         return cuda_fail(s, f);
+    } catch (const NcclFail& f) {
+        s->cur = &s->ctx;
+        return nccl_fail(s, f);
+    } catch (const std::exception& e) {
+        s->cur = &s->ctx;
+        return fail(s, TLPB200_INTERNAL, e.what());
     }
 }
 
@@ -1299,6 +1499,9 @@ int tlpb200_update_begin(tlpb200_solver* s, const double* theta_inv, const doubl
     } catch (const CudaFail& f) {
         s->cur = &s->ctx;
         return cuda_fail(s, f);
+    } catch (const std::exception& e) {
+        s->cur = &s->ctx;
+        return fail(s, TLPB200_INTERNAL, e.what());
     }
 }
 
@@ -1327,6 +1530,9 @@ int tlpb200_update_end(tlpb200_solver* s, int64_t* bad_pivot) {
     } catch (const CudaFail& f) {
         s->cur = &s->ctx;
         return cuda_fail(s, f);
+    } catch (const std::exception& e) {
+        s->cur = &s->ctx;
+        return fail(s, TLPB200_INTERNAL, e.what());
     }
 }
 
@@ -1354,6 +1560,9 @@ int tlpb200_solve_begin(tlpb200_solver* s, const double* xi_p, const double* xi_
     } catch (const CudaFail& f) {
         s->cur = &s->ctx;
         return cuda_fail(s, f);
+    } catch (const std::exception& e) {
+        s->cur = &s->ctx;
+        return fail(s, TLPB200_INTERNAL, e.what());
     }
 }
 
@@ -1385,6 +1594,9 @@ int tlpb200_solve_mid(tlpb200_solver* s) {
     } catch (const CudaFail& f) {
         s->cur = &s->ctx;
         return cuda_fail(s, f);
+    } catch (const std::exception& e) {
+        s->cur = &s->ctx;
+        return fail(s, TLPB200_INTERNAL, e.what());
     }
 }
 
@@ -1411,6 +1623,106 @@ int tlpb200_solve_end(tlpb200_solver* s, double* dx, double* dy) {
         return TLPB200_OK;
     } catch (const CudaFail& f) {
         return cuda_fail(s, f);
+    } catch (const NcclFail& f) {
+        s->cur = &s->ctx;
+        return nccl_fail(s, f);
+    } catch (const std::exception& e) {
+        s->cur = &s->ctx;
+        return fail(s, TLPB200_INTERNAL, e.what());
+    }
+}
+
+// ---- in-library collectives: NCCL over NVLink on the solver's stream ------------------------------------------------------
+int tlpb200_comm_unique_id(void* out128) {
+    if (!out128) return TLPB200_BAD_ARG;
+    NcclApi& api = nccl_api();
+    if (!api.h) return TLPB200_NCCL;
+    ncclUniqueId id;
+    if (api.GetUniqueId(&id) != ncclSuccess) return TLPB200_NCCL;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    std::memcpy(out128, &id, sizeof id);
+    return TLPB200_OK;
+}
+
+int tlpb200_comm_init(tlpb200_solver* s, const void* id128) {
+    REQUIRE_DEVICE(s);
+    if (!id128) return fail(s, TLPB200_BAD_ARG, "tlpb200_comm_init: null id");
+    if (s->nranks < 2) return fail(s, TLPB200_BAD_ARG, "tlpb200_comm_init: solver was not created with nranks > 1");
+    if (s->comm) return TLPB200_OK;
+    NcclApi& api = nccl_api();
+    if (!api.h) return fail(s, TLPB200_NCCL, api.err);
+    try {
+        CK(cudaSetDevice(s->device));
+        ncclUniqueId id;
+        std::memcpy(&id, id128, sizeof id);
+        NK(api.CommInitRank(&s->comm, s->nranks, id, s->rank));
+        // first collective outside any stream capture: NCCL sets up its channels / connections lazily
+        CK(cudaMemsetAsync(s->d_info_tmp, 0, 4 * sizeof(int32_t), s->stream));
+        NK(api.AllReduce(s->d_info_tmp, s->d_info_tmp, 4, ncclInt32, ncclMax, s->comm, s->stream));
+        if (s->ntop > 0) {
+            CK(cudaMemsetAsync(s->d_tbuf, 0, (size_t)s->ntop * 8, s->stream));
+            NK(api.AllReduce(s->d_tbuf, s->d_tbuf, (size_t)s->ntop, ncclFloat64, ncclSum, s->comm, s->stream));
+        }
+        NK(api.AllReduce(s->ctx.wk, s->ctx.wk, (size_t)s->sym.N, ncclFloat64, ncclSum, s->comm, s->stream));
+        const int64_t top_cnt = s->sym.lx_size - s->top_begin;
+        if (top_cnt > 0) NK(api.AllReduce(s->ctx.Lx + s->top_begin, s->ctx.Lx + s->top_begin, (size_t)top_cnt, ncclFloat64, ncclSum, s->comm, s->stream));
+        CK(cudaStreamSynchronize(s->stream));
+        destroy_graphs(s);
+        return TLPB200_OK;
+    } catch (const CudaFail& f) {
+        return cuda_fail(s, f);
+    } catch (const NcclFail& f) {
+        return nccl_fail(s, f);
+    }
+}
+
+/* mean time [ms] of the collectives of one sharded update! / solve!, each timed alone over `reps` back-to-back calls with CUDA
+   events on the solver's stream: ms[0] = all-reduce of the top panels (update!), ms[1] = all-reduce of the separator entries
+   (solve!), ms[2] = all-reduce of the solution vector (solve!), ms[3] = status all-reduce (update!); bytes[0..3] = their payloads */
+int tlpb200_comm_profile(tlpb200_solver* s, int32_t reps, float* ms, int64_t* bytes) {
+    REQUIRE_DEVICE(s);
+    if (!s->comm) return fail(s, TLPB200_BAD_ARG, "tlpb200_comm_profile: no communicator (tlpb200_comm_init)");
+    if (reps < 1) reps = 1;
+    NcclApi& api = nccl_api();
+    try {
+        CK(cudaSetDevice(s->device));
+        const int64_t top_cnt = s->sym.lx_size - s->top_begin;
+        // scratch copies so that the factor / work vector are left alone
+        double* scratch = nullptr;
+        const size_t cnt = (size_t)std::max<int64_t>(std::max<int64_t>(top_cnt, s->sym.N), 4);
+        CK(cudaMalloc((void**)&scratch, cnt * 8));
+        CK(cudaMemsetAsync(scratch, 0, cnt * 8, s->stream));
+        const size_t sizes[4] = {(size_t)top_cnt, (size_t)s->ntop, (size_t)s->sym.N, 4};
+        cudaEvent_t e0, e1;
+        CK(cudaEventCreate(&e0));
+        CK(cudaEventCreate(&e1));
+        for (int k = 0; k < 4; ++k) {
+            if (bytes) bytes[k] = (int64_t)sizes[k] * (k == 3 ? 4 : 8);
+            if (ms) ms[k] = 0.f;
+            if (sizes[k] == 0) continue;
+            for (int w = 0; w < 2; ++w) {
+                if (k == 3) NK(api.AllReduce(scratch, scratch, 4, ncclInt32, ncclMax, s->comm, s->stream));
+                else NK(api.AllReduce(scratch, scratch, sizes[k], ncclFloat64, ncclSum, s->comm, s->stream));
+            }
+            CK(cudaEventRecord(e0, s->stream));
+            for (int r = 0; r < reps; ++r) {
+                if (k == 3) NK(api.AllReduce(scratch, scratch, 4, ncclInt32, ncclMax, s->comm, s->stream));
+                else NK(api.AllReduce(scratch, scratch, sizes[k], ncclFloat64, ncclSum, s->comm, s->stream));
+            }
+            CK(cudaEventRecord(e1, s->stream));
+            CK(cudaStreamSynchronize(s->stream));
+            float t = 0;
+            CK(cudaEventElapsedTime(&t, e0, e1));
+            if (ms) ms[k] = t / (float)reps;
+        }
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        cudaFree(scratch);
+        return TLPB200_OK;
+    } catch (const CudaFail& f) {
+        return cuda_fail(s, f);
+    } catch (const NcclFail& f) {
+        return nccl_fail(s, f);
     }
 }
 
@@ -1441,6 +1753,7 @@ void tlpb200_destroy(tlpb200_solver* s) {
         cudaSetDevice(s->device);
         cudaStreamSynchronize(s->stream);
         destroy_graphs(s);
+        if (s->comm && nccl_api().h) { nccl_api().CommDestroy(s->comm); s->comm = nullptr; }
         for (void* p : s->allocs) cudaFree(p);
         if (s->h_pin) cudaFreeHost(s->h_pin);
         if (s->h_info) cudaFreeHost(s->h_info);

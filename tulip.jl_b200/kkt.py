@@ -177,6 +177,11 @@ class B200KKTSolver:
     def solve_multi(self, DX, DY, XI_P, XI_D):
         """nrhs right-hand sides, one per *row* of the (nrhs, n)/(nrhs, m) C-contiguous arrays."""
         nrhs = XI_P.shape[0]
+        XI_P = np.ascontiguousarray(XI_P, dtype=np.float64); XI_D = np.ascontiguousarray(XI_D, dtype=np.float64)
+        if XI_P.shape != (nrhs, self.m) or XI_D.shape != (nrhs, self.n) or DX.shape != (nrhs, self.n) or DY.shape != (nrhs, self.m):
+            raise DimensionMismatch("solve_multi: expected (nrhs, m) / (nrhs, n) arrays")
+        if not (DX.flags.c_contiguous and DY.flags.c_contiguous and DX.dtype == np.float64 and DY.dtype == np.float64):
+            raise TypeError("DX, DY must be C-contiguous float64 arrays (they are overwritten in place)")
         rc = _lib.load().tlpb200_solve(self._h, _dp(DX), _dp(DY), _dp(np.ascontiguousarray(XI_P)),
                                        _dp(np.ascontiguousarray(XI_D)), nrhs, self.n, self.m)
         if rc != _lib.OK:
