@@ -195,6 +195,55 @@ int tlpb200_comm_init(tlpb200_solver* s, const void* id128);
  * [1] separator entries, [2] solution vector, [3] status words; bytes[] = their payloads.  Collective call. */
 int tlpb200_comm_profile(tlpb200_solver* s, int32_t reps, float* ms /* 4 */, int64_t* bytes /* 4 */);
 
+/* ---- device-resident IPM iteration ------------------------------------------------------------------
+ * The caller of the KKT path -- Tulip's homogeneous self-dual IPM, /root/reference/src/IPM/HSD/HSD.jl:203-350 (main loop,
+ * residuals :77-128, status tests :136-196) and src/IPM/HSD/step.jl:10-401 (compute_step!) -- with every vector resident in
+ * HBM: theta / regularisation schedule / rhs builds / recoveries / step lengths / corrector targets are fused elementwise
+ * kernels, update! / solve! are the same device sequences as above, the host reads back one block of scalars per decision.
+ * The LP is the standard form the KKT boundary sees (A x = b, l <= x <= u; ipmdata.jl:6-12) with the A given to
+ * tlpb200_create.  With nranks > 1 (after tlpb200_comm_init) every rank runs the same loop on the sharded factorisation. */
+enum {
+    TLPB200_TRM_UNKNOWN = 0,           /* keep iterating                       (status.jl: Trm_Unknown) */
+    TLPB200_TRM_OPTIMAL = 1,           /* HSD.jl:161-166 */
+    TLPB200_TRM_PRIMAL_INFEASIBLE = 2, /* HSD.jl:181-192 */
+    TLPB200_TRM_DUAL_INFEASIBLE = 3,   /* HSD.jl:170-179 */
+    TLPB200_TRM_ITERATION_LIMIT = 4,   /* HSD.jl:303-305 */
+    TLPB200_TRM_TIME_LIMIT = 5,        /* HSD.jl:306-308 */
+    TLPB200_TRM_NUMERICAL_PROBLEM = 6, /* HSD.jl:321-326 (factorisation could not be saved, step.jl:51) */
+    TLPB200_TRM_MEMORY_LIMIT = 7       /* HSD.jl:327 */
+};
+typedef struct tlpb200_hsd_options {   /* src/IPM/options.jl:1-25 */
+    int32_t iterations_limit;          /* 100 */
+    int32_t correction_limit;          /* 3 */
+    double time_limit;                 /* seconds, inf */
+    double tol_pfeas, tol_dfeas, tol_rgap, tol_ifeas;   /* sqrt(eps) */
+    double step_damp;                  /* 0.9995 */
+    double gamma_min;                  /* 0.1 */
+    double centrality_outlier;         /* 0.1 */
+    double preg_min, dreg_min;         /* sqrt(eps) */
+} tlpb200_hsd_options;
+typedef struct tlpb200_hsd_info {
+    int32_t status, niter;
+    double pobj, dobj;                 /* primal / dual objective of the current iterate (HSD.jl:126-127) */
+    double rp_nrm, rl_nrm, ru_nrm, rd_nrm, rg_nrm;   /* residual infinity norms (HSD.jl:119-123) */
+    double mu, tau, kappa;
+    int64_t n_update, n_solve;         /* KKT calls so far */
+    double ms_update, ms_solve;        /* CUDA-event time of those calls: the reference's "Factorization" / "KKT" timer sections */
+    double seconds_total;              /* wall time of tlpb200_hsd_optimize */
+} tlpb200_hsd_info;
+void tlpb200_hsd_default_options(tlpb200_hsd_options* opt);
+int tlpb200_hsd_create(tlpb200_solver* s, const double* b /* m */, const double* c /* n */, const double* l /* n, -inf allowed */,
+                       const double* u /* n, +inf allowed */, double c0);
+int tlpb200_hsd_reset(tlpb200_solver* s);   /* next iterate call starts again from the start point (HSD.jl:238-247) */
+/* one pass of the main-loop body: residuals + status tests, then compute_step! unless the run is over */
+int tlpb200_hsd_iterate(tlpb200_solver* s, const tlpb200_hsd_options* opt, tlpb200_hsd_info* info);
+/* ipm_optimize!: from the start point until a termination status */
+int tlpb200_hsd_optimize(tlpb200_solver* s, const tlpb200_hsd_options* opt, tlpb200_hsd_info* info);
+/* copy the iterate to the host (any pointer may be NULL); tau_kappa[2] */
+int tlpb200_hsd_get_point(tlpb200_solver* s, double* x, double* xl, double* xu, double* y, double* zl, double* zu, double* tau_kappa);
+/* rows of 8 doubles {iter, pobj, dobj, pfeas, dfeas, gfeas, mu, tau}, one per pass (the reference's log line, HSD.jl:266-287) */
+int tlpb200_hsd_get_log(tlpb200_solver* s, double* out, int64_t* rows);
+
 /* K1 dense-column path: number and (0-based) indices of the columns kept out of the sparse factor */
 int tlpb200_get_dense_cols(const tlpb200_solver* s, int32_t* count, int64_t* cols /* may be NULL */);
 

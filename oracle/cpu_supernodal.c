@@ -79,11 +79,47 @@ int cpu_sn_scatter(int32_t N, int32_t nsuper, const int32_t* sn_first, const int
     return 0;
 }
 
+/* C[i, j] = beta C[i, j] + alpha sum_k A[i, k] A[j, k]  for j < ncols, j <= i < nrows (lower trapezoid; A is nrows x k).
+ * One dsyrk + one dgemm when the output is small; block columns of CB otherwise: SciPy's OpenBLAS (0.3.x, LP64) crashes in
+ * dsyrk_thread_LN / dpotrf_L_parallel once n * ld of a single call passes 2^31 (reproduced at n = 50 870), so no single
+ * call is allowed to address that much. */
+static void syrk_gemm_lower(int nrows, int ncols, int k, double alpha, const double* A, int lda, double beta, double* C, int ldc) {
+    const int CB = ((double)ncols * (double)ldc < 1.5e9 && (double)nrows * (double)lda < 1.5e9) ? ncols : 2048;
+    for (int c0 = 0; c0 < ncols; c0 += CB) {
+        const int cw = (ncols - c0 < CB) ? ncols - c0 : CB;
+        double* Cc = C + (size_t)c0 * ldc + c0;
+        p_dsyrk("L", "N", &cw, &k, &alpha, A + c0, &lda, &beta, Cc, &ldc);
+        const int nr = nrows - c0 - cw;
+        if (nr > 0) p_dgemm("N", "T", &nr, &cw, &k, &alpha, A + c0 + cw, &lda, A + c0, &lda, &beta, Cc + cw, &ldc);
+    }
+}
+
 /* signed factorisation of an nrow x ns trapezoid (column-major, ld), K = L S L' */
 static int factor_panel(double* P, int ld, int nrow, int ns, const int8_t* sg, int32_t gcol0, int32_t* bad) {
     int allpos = 1, info = 0;
     for (int j = 0; j < ns; ++j) if (sg[j] < 0) { allpos = 0; break; }
     const double one = 1.0;
+    if (allpos && (double)ns * (double)ld >= 1.5e9) {
+        /* see syrk_gemm_lower: a panel this large (the north-star config's root supernode has 84 770 columns) is factored by
+         * the textbook blocked right-looking algorithm on top of calls that each address < 2^31 elements: dpotrf on a NB x NB
+         * diagonal block, dtrsm on the rows below, block-column dsyrk / dgemm on the trailing part. */
+        const int NB = 2048;
+        const double mone = -1.0;
+        for (int jb = 0; jb < ns; jb += NB) {
+            const int nb = (ns - jb < NB) ? ns - jb : NB;
+            double* D = P + (size_t)jb * ld + jb;
+            p_dpotrf("L", &nb, D, &ld, &info);
+            if (info != 0) { if (*bad < 0) *bad = gcol0 + jb + (info > 0 ? info - 1 : 0); return 1; }
+            for (int j = 0; j < nb; ++j) if (!(D[(size_t)j * ld + j] > 0.0)) { if (*bad < 0) *bad = gcol0 + jb + j; return 1; }
+            const int below = nrow - jb - nb;
+            if (below > 0) {
+                p_dtrsm("R", "L", "T", "N", &below, &nb, &one, D, &ld, D + nb, &ld);
+                const int ntr = ns - jb - nb;        /* trailing columns of the panel */
+                if (ntr > 0) syrk_gemm_lower(below, ntr, nb, mone, D + nb, ld, one, D + (size_t)nb * ld + nb, ld);
+            }
+        }
+        return 0;
+    }
     if (allpos) {
         p_dpotrf("L", &ns, P, &ld, &info);
         if (info != 0) { if (*bad < 0) *bad = gcol0 + (info > 0 ? info - 1 : 0); return 1; }
@@ -173,9 +209,7 @@ int cpu_sn_factor(int32_t N, int32_t nsuper, const int32_t* sn_first, const int6
             for (int j = 0; j < nsd; ++j) if (sign[fd + j] < 0) { mixed = 1; break; }
             const double one = 1.0, zero = 0.0;
             if (!mixed) {
-                p_dsyrk("L", "N", &nd1, &nsd, &one, Ld, &nrowd, &zero, C, &nd);
-                const int nd2 = nd - nd1;
-                if (nd2 > 0) p_dgemm("N", "T", &nd2, &nd1, &nsd, &one, Ld + nd1, &nrowd, Ld, &nrowd, &zero, C + nd1, &nd);
+                syrk_gemm_lower(nd, nd1, nsd, one, Ld, nrowd, zero, C, nd);
             } else {
                 if ((size_t)nd1 * nsd > wsize) { free(W); wsize = (size_t)nd1 * nsd; W = (double*)malloc(sizeof(double) * wsize); if (!W) { rc = 2; goto done; } }
                 for (int j = 0; j < nsd; ++j) {

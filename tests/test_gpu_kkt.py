@@ -122,11 +122,10 @@ def test_solve_parity_vs_oracle(cfg, sysname):
         kappa = float(np.linalg.cond(_kkt_matrix(A, sysname, theta, regP, regD)))
         tol = 1e-8
         if 10 * kappa * np.finfo(float).eps > tol:
-            tol = 10 * kappa * np.finfo(float).eps
+            tol = min(10 * kappa * np.finfo(float).eps, 1e-5)      # never looser than 1e-5, whatever the conditioning
             ILL_CONDITIONED_CASES[(str(cfg), sysname, spread, reg)] = (kappa, tol, max(ex, ey))
             print(f"ill-conditioned case cfg{cfg}-mini {sysname} spread={spread} reg={reg}: cond_2(K)={kappa:.3e}, "
                   f"bar {tol:.2e}, measured {max(ex, ey):.2e}")
-        assert tol <= 1e-4, ("condition number beyond what the test is meant to cover", kappa)
         assert ex <= tol and ey <= tol, (ex, ey, kappa, tol)
 
 

@@ -25,6 +25,25 @@ class Options(C.Structure):
                 ("ozaki_ncol", C.c_int32), ("reserved", C.c_int32 * 4)]
 
 
+class HSDOptions(C.Structure):
+    _fields_ = [("iterations_limit", C.c_int32), ("correction_limit", C.c_int32), ("time_limit", C.c_double),
+                ("tol_pfeas", C.c_double), ("tol_dfeas", C.c_double), ("tol_rgap", C.c_double), ("tol_ifeas", C.c_double),
+                ("step_damp", C.c_double), ("gamma_min", C.c_double), ("centrality_outlier", C.c_double),
+                ("preg_min", C.c_double), ("dreg_min", C.c_double)]
+
+
+class HSDInfo(C.Structure):
+    _fields_ = [("status", C.c_int32), ("niter", C.c_int32), ("pobj", C.c_double), ("dobj", C.c_double),
+                ("rp_nrm", C.c_double), ("rl_nrm", C.c_double), ("ru_nrm", C.c_double), ("rd_nrm", C.c_double),
+                ("rg_nrm", C.c_double), ("mu", C.c_double), ("tau", C.c_double), ("kappa", C.c_double),
+                ("n_update", C.c_int64), ("n_solve", C.c_int64), ("ms_update", C.c_double), ("ms_solve", C.c_double),
+                ("seconds_total", C.c_double)]
+
+
+TRM_STATUS = ["Trm_Unknown", "Trm_Optimal", "Trm_PrimalInfeasible", "Trm_DualInfeasible", "Trm_IterationLimit",
+              "Trm_TimeLimit", "Trm_NumericalProblem", "Trm_MemoryLimit"]
+
+
 class Stats(C.Structure):
     _fields_ = [("m", C.c_int64), ("n", C.c_int64), ("nnzA", C.c_int64), ("order", C.c_int64),
                 ("nnzL", C.c_int64), ("nnzL_stored", C.c_int64), ("flops", C.c_double),
@@ -55,7 +74,9 @@ KERNEL_CLASSES = ["assemble", "small_factor", "diag_factor", "trsm", "update", "
 # every symbol include/tlpb200.h declares (tests check that the library exports all of them)
 SYMBOLS = [
     "tlpb200_default_options", "tlpb200_create", "tlpb200_update", "tlpb200_update_dev",
-    "tlpb200_update_status", "tlpb200_solve", "tlpb200_solve_dev", "tlpb200_solve_status", "tlpb200_debug_raise_timeout", "tlpb200_comm_unique_id", "tlpb200_comm_init", "tlpb200_comm_profile", "tlpb200_set_stream",
+    "tlpb200_update_status", "tlpb200_solve", "tlpb200_solve_dev", "tlpb200_solve_status", "tlpb200_debug_raise_timeout", "tlpb200_comm_unique_id", "tlpb200_comm_init", "tlpb200_comm_profile",
+    "tlpb200_hsd_default_options", "tlpb200_hsd_create", "tlpb200_hsd_reset", "tlpb200_hsd_iterate", "tlpb200_hsd_optimize",
+    "tlpb200_hsd_get_point", "tlpb200_hsd_get_log", "tlpb200_set_stream",
     "tlpb200_synchronize", "tlpb200_set_profiling", "tlpb200_stats_get", "tlpb200_get_symbolic",
     "tlpb200_get_structure", "tlpb200_debug_assemble", "tlpb200_debug_get_lx", "tlpb200_last_error",
     "tlpb200_backend_name", "tlpb200_linear_system", "tlpb200_destroy",
@@ -98,6 +119,17 @@ def load():
     lib.tlpb200_comm_init.restype = C.c_int
     lib.tlpb200_comm_profile.argtypes = [p, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_int64)]
     lib.tlpb200_comm_profile.restype = C.c_int
+    lib.tlpb200_hsd_default_options.argtypes = [C.POINTER(HSDOptions)]
+    lib.tlpb200_hsd_default_options.restype = None
+    lib.tlpb200_hsd_create.argtypes = [p, dp, dp, dp, dp, C.c_double]
+    lib.tlpb200_hsd_reset.argtypes = [p]
+    lib.tlpb200_hsd_iterate.argtypes = [p, C.POINTER(HSDOptions), C.POINTER(HSDInfo)]
+    lib.tlpb200_hsd_optimize.argtypes = [p, C.POINTER(HSDOptions), C.POINTER(HSDInfo)]
+    lib.tlpb200_hsd_get_point.argtypes = [p, dp, dp, dp, dp, dp, dp, dp]
+    lib.tlpb200_hsd_get_log.argtypes = [p, dp, C.POINTER(C.c_int64)]
+    for name in ("tlpb200_hsd_create", "tlpb200_hsd_reset", "tlpb200_hsd_iterate", "tlpb200_hsd_optimize",
+                 "tlpb200_hsd_get_point", "tlpb200_hsd_get_log"):
+        getattr(lib, name).restype = C.c_int
     lib.tlpb200_set_stream.argtypes = [p, p]
     lib.tlpb200_synchronize.argtypes = [p]
     lib.tlpb200_set_profiling.argtypes = [p, C.c_int]
