@@ -58,7 +58,10 @@ typedef struct tlpb200_options {
     int32_t ozaki_ncol;          /* K1, single GPU: supernodes with at least this many columns run their far Schur updates on
                                     the tcgen05 int8 tensor-core path (exact digit-plane products, FP64-grade result);
                                     0 = default (1024), < 0 = off (FP64 DMMA path everywhere) */
-    int32_t reserved[4];
+    int32_t refine_steps;        /* iterative-refinement steps inside solve! on the factored KKT system (the reference
+                                    has only TODOs, spd.jl:68 / sqd.jl:72): 0 = off (default, the reference's single solve), <= 8;
+                                    single GPU.  The dense-column path always refines (its Woodbury solve is the preconditioner). */
+    int32_t reserved[3];
 } tlpb200_options;
 
 #define TLPB200_NCLASS 24
@@ -83,7 +86,7 @@ typedef struct tlpb200_stats {
     /* profiling mode: CUDA-event time and launch count per kernel class of the last update!/solve!
      * 0 assemble  1 small_factor  2 diag_factor  3 trsm  4 update  5 rhs+recover
      * 6 fwd_small 7 fwd_large 8 -  9 bwd_large 10 invert_diag 11 bwd_small */
-    double ms_class[TLPB200_NCLASS];   /* ... 12 dense_cols 13 pack_big 14 fwd_big 15 bwd_big 16 oz_slice 17 oz_update 18 collectives */
+    double ms_class[TLPB200_NCLASS];   /* ... 12 dense_cols 13 pack_big 14 fwd_big 15 bwd_big 16 oz_slice 17 oz_update 18 collectives 19 refinement */
     int64_t n_class[TLPB200_NCLASS];
     double flops_update_oz; /* algorithmic flops of one update! done by the tcgen05 int8 tasks (not part of flops_update_ext) */
     int64_t oz_tasks;       /* tcgen05 tasks per update! */

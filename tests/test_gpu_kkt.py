@@ -471,3 +471,31 @@ def test_solve_timeout_flag_is_reported_and_cleared():
     k.solve(dx, dy, np.ones(m), np.ones(n))
     rp, rd = kkt_ref.kkt_residuals(A, np.ones(n), np.ones(n), np.ones(m), dx, dy, np.ones(m), np.ones(n))
     assert rp <= SQRT_EPS and rd <= SQRT_EPS
+
+
+@pytest.mark.parametrize("sysname", ["K1", "K2"])
+def test_iterative_refinement_option(sysname):
+    """refine_steps > 0 re-solves on the FP64 residual of the factored KKT system; on ill-conditioned data the
+    KKT residuals (test.jl:39-40 formulas) must not get worse and the solution must stay within the per-call parity bar."""
+    lp = lpgen.config(3 if sysname == "K2" else 2, mini=True)
+    A = lp.A
+    m, n = A.shape
+    rng = np.random.default_rng(31)
+    theta = np.exp(rng.uniform(-7, 7, n)); regP = np.full(n, 1e-7); regD = np.full(m, 1e-7)
+    xi_p = rng.standard_normal(m); xi_d = rng.standard_normal(n)
+    res = []
+    sols = []
+    for steps in (0, 2):
+        k = pkg.setup(A, SYSTEMS[sysname](), pkg.Backend(refine_steps=steps))
+        k.update(theta, regP, regD)
+        dx = np.zeros(n); dy = np.zeros(m)
+        k.solve(dx, dy, xi_p, xi_d)
+        res.append(max(kkt_ref.kkt_residuals(A, theta, regP, regD, dx, dy, xi_p, xi_d)))
+        sols.append(np.concatenate([dx, dy]))
+        if steps:
+            assert k.stats()["launches_solve"] > launches0      # the refinement sweeps were really enqueued
+        launches0 = k.stats()["launches_solve"]
+    scale = max(1.0, np.abs(sols[0]).max())
+    assert res[1] <= max(2.0 * res[0], 1e-12 * scale), res
+    assert res[1] <= SQRT_EPS * scale
+    assert np.abs(sols[1] - sols[0]).max() <= 1e-5 * np.abs(sols[0]).max()

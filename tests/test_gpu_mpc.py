@@ -1,0 +1,56 @@
+"""GPU tests: the B200 KKT backend under the reference's second client, Mehrotra's predictor-corrector (SURVEY 8f-4;
+/root/reference/src/IPM/MPC/MPC.jl:359-363 two start-point solves after one update!, MPC/step.jl:10-123), starting from
+general-form LPs through the standard-form build (ipmdata.jl:64-173)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import tlpb200_loader
+from golden.lpex import LPEX
+from oracle import kkt_ref
+
+pkg = tlpb200_loader.load()
+from tulip_jl_b200 import ipmdata, lpgen, mpc  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+SQRT_EPS = float(np.sqrt(np.finfo(float).eps))
+SYSTEMS = {"K1": pkg.K1, "K2": pkg.K2}
+
+
+@pytest.mark.parametrize("name", ["lpex_opt", "lpex_freevars"])
+@pytest.mark.parametrize("sysname", ["K1", "K2"])
+def test_mpc_example_lps_on_device_backend(name, sysname):
+    """test/examples.jl:5-19, IPM_Factory = Factory(MPC), KKT_Backend = TlpB200"""
+    lp = LPEX[name]
+    A0 = sp.coo_matrix((lp["vals"], (lp["rows"], lp["cols"])), shape=(lp["ncon"], lp["nvar"]))
+    dat = ipmdata.standard_form(A0, lp["lcon"], lp["ucon"], lp["lvar"], lp["uvar"], lp["obj"], lp["obj0"], lp["objsense"])
+    kkt = pkg.setup(dat.A, SYSTEMS[sysname](), pkg.Backend())
+    h = mpc.MPC(dat.A, dat.b, dat.c, dat.l, dat.u, kkt, c0=dat.c0, objsense=dat.objsense)
+    assert h.optimize() == "Trm_Optimal"
+    exp = lp["expect"]
+    tol = 100 * SQRT_EPS
+    assert abs(h.primal_objective - exp["obj"]) <= tol * (1 + abs(exp["obj"]))
+    if "x" in exp:
+        np.testing.assert_allclose(h.x[:lp["nvar"]], exp["x"], atol=tol, rtol=tol)
+    if "y" in exp:
+        np.testing.assert_allclose(h.y, exp["y"], atol=tol, rtol=tol)
+
+
+@pytest.mark.parametrize("cfg,sysname", [(2, "K1"), (3, "K2"), (4, "K1"), (5, "K1")])
+def test_mpc_device_backend_matches_oracle_backend(cfg, sysname):
+    """same MPC driver, device KKT vs oracle KKT: same iteration count (+-1) and objective to 1e-8 with tightened tolerances"""
+    from tulip_jl_b200 import hsd
+    lp = lpgen.config(cfg, mini=True)
+    P = dict(TolerancePFeas=1e-10, ToleranceDFeas=1e-10, ToleranceRGap=1e-10)
+    o = kkt_ref.SparseK1(lp.A) if sysname == "K1" else kkt_ref.SparseK2(lp.A)
+    ref = mpc.MPC(lp.A, lp.b, lp.c, lp.l, lp.u, o, params=hsd.IPMOptions(**P))
+    ref.optimize()
+    kkt = pkg.setup(lp.A, SYSTEMS[sysname](), pkg.Backend())
+    h = mpc.MPC(lp.A, lp.b, lp.c, lp.l, lp.u, kkt, params=hsd.IPMOptions(**P))
+    h.optimize()
+    assert h.status == ref.status == "Trm_Optimal"
+    assert abs(h.niter - ref.niter) <= 1
+    assert abs(h.primal_objective - ref.primal_objective) <= 1e-8 * (1 + abs(ref.primal_objective))
+    assert abs(h.dual_objective - ref.dual_objective) <= 1e-8 * (1 + abs(ref.dual_objective))
+    st = kkt.stats()
+    assert st["n_update"] == h.n_update and st["n_solve"] == h.n_solve          # every KKT call went to the device

@@ -7,7 +7,7 @@ triangular solves -- as hand-written CUDA for sm_100a behind a C ABI (include/tl
 The directory name contains a dot, so it is loaded through ``tlpb200_loader`` (repo root), which
 registers it under the importable name ``tulip_jl_b200``.
 """
-from . import _lib, hsd, hsd_device, kkt, lpgen  # noqa: F401
+from . import _lib, hsd, hsd_device, ipmdata, kkt, lpgen, mpc  # noqa: F401
 from .hsd_device import DeviceHSD  # noqa: F401
 from .kkt import (K1, K2, Backend, B200KKTSolver, DefaultKKTSystem, DimensionMismatch,  # noqa: F401
                   OutOfMemoryError, PosDefException, TlpB200Error, arithmetic, backend, linear_system,
@@ -15,4 +15,4 @@ from .kkt import (K1, K2, Backend, B200KKTSolver, DefaultKKTSystem, DimensionMis
 
 __all__ = ["K1", "K2", "Backend", "B200KKTSolver", "DefaultKKTSystem", "setup", "update_", "solve_",
            "arithmetic", "backend", "linear_system", "PosDefException", "DimensionMismatch",
-           "OutOfMemoryError", "TlpB200Error", "lpgen", "kkt", "hsd", "hsd_device", "DeviceHSD"]
+           "OutOfMemoryError", "TlpB200Error", "lpgen", "kkt", "hsd", "hsd_device", "DeviceHSD", "mpc", "ipmdata"]

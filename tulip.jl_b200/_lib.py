@@ -22,7 +22,7 @@ class Options(C.Structure):
                 ("small_elems", C.c_int32), ("relax_always", C.c_int32), ("use_graph", C.c_int32),
                 ("analyze_only", C.c_int32), ("rank", C.c_int32), ("nranks", C.c_int32),
                 ("dense_col_threshold", C.c_int32), ("dense_solve_ncol", C.c_int32),
-                ("ozaki_ncol", C.c_int32), ("reserved", C.c_int32 * 4)]
+                ("ozaki_ncol", C.c_int32), ("refine_steps", C.c_int32), ("reserved", C.c_int32 * 3)]
 
 
 class HSDOptions(C.Structure):
@@ -68,7 +68,7 @@ class Stats(C.Structure):
 
 KERNEL_CLASSES = ["assemble", "small_factor", "diag_factor", "trsm", "update", "rhs_recover",
                   "fwd_small", "fwd_large", "update128", "bwd_large", "invert_diag", "bwd_small", "dense_cols",
-                  "pack_big", "fwd_big", "bwd_big", "oz_slice", "oz_update", "comm"]
+                  "pack_big", "fwd_big", "bwd_big", "oz_slice", "oz_update", "comm", "refine"]
 
 
 # every symbol include/tlpb200.h declares (tests check that the library exports all of them)

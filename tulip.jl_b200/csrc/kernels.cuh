@@ -112,6 +112,8 @@ struct DevMat;
 void launch_dc_residual(const DevCtx& c, const DevMat& A, const double* d, const double* regD, const double* xi, const double* y,
                         double* tn, cudaStream_t st);
 void launch_dc_axpy(const DevCtx& c, const double* y, cudaStream_t st);
+void launch_k2_residual(const DevCtx& c, const DevMat& A, const double* theta, const double* regP, const double* regD, const double* xi,
+                        const double* y, cudaStream_t st);
 
 // ---- launchers (all asynchronous on `st`) ---------------------------------------------------
 void launch_compute_d(const double* theta, const double* regP, double* d, int64_t n, cudaStream_t st);

@@ -127,6 +127,29 @@ __global__ void k_dc_axpy(DevCtx c, const double* __restrict__ y) {
     const int32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q < c.N) c.wk[q] += y[q];
 }
+// K2: r = [xi_d; xi_p] - [-(theta + Rp) A'; A Rd] [dx; dy]  (systems.jl:8-32 signs), everything in permuted order:
+// xi / y are the saved right-hand side and the current solution as laid out in wk (index iperm[v], v < n: x-block)
+__global__ void k_k2_residual(DevCtx c, DevMat A, const double* __restrict__ theta, const double* __restrict__ regP,
+                              const double* __restrict__ regD, const double* __restrict__ xi, const double* __restrict__ y) {
+    const int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (v >= A.n + A.m) return;
+    const int32_t q = c.iperm[v];
+    double r = xi[q];
+    if (v < A.n) {
+        r += (theta[v] + regP[v]) * y[q];
+        for (int64_t p = A.colptr[v]; p < A.colptr[v + 1]; ++p) r -= A.val[p] * y[c.iperm[A.n + A.rowidx[p]]];
+    } else {
+        const int64_t i = v - A.n;
+        r -= regD[i] * y[q];
+        for (int64_t p = A.rowptr[i]; p < A.rowptr[i + 1]; ++p) r -= A.rval[p] * y[c.iperm[A.colidx[p]]];
+    }
+    c.wk[q] = r;
+}
+void launch_k2_residual(const DevCtx& c, const DevMat& A, const double* theta, const double* regP, const double* regD, const double* xi,
+                        const double* y, cudaStream_t st) {
+    if (A.n + A.m > 0) k_k2_residual<<<(unsigned)((A.n + A.m + 127) / 128), 128, 0, st>>>(c, A, theta, regP, regD, xi, y);
+}
+
 void launch_dc_residual(const DevCtx& c, const DevMat& A, const double* d, const double* regD, const double* xi, const double* y,
                         double* tn, cudaStream_t st) {
     k_dc_at_y<<<(unsigned)((A.n + 127) / 128), 128, 0, st>>>(c, A, d, y, tn);

@@ -426,9 +426,25 @@ void enqueue_recover(tlpb200_solver* s, const double* xid, double* dx, double* d
 void enqueue_solve(tlpb200_solver* s, const double* xip, const double* xid, double* dx, double* dy, int64_t& count) {
     enqueue_rhs(s, xip, xid, count);
     const size_t nb = (size_t)s->sym.N * 8;
-    if (s->dc.nd > 0) CK(cudaMemcpyAsync(s->dc_xi, s->ctx.wk, nb, cudaMemcpyDeviceToDevice, s->stream));
+    if (s->dc.nd > 0 || s->refine > 0) CK(cudaMemcpyAsync(s->dc_xi, s->ctx.wk, nb, cudaMemcpyDeviceToDevice, s->stream));
     enqueue_fwd(s, count);
     enqueue_bwd(s, count);
+    if (s->dc.nd == 0 && s->refine > 0) {
+        // iterative refinement inside solve! (the reference only has TODOs: spd.jl:68, sqd.jl:72): residual of the
+        // KKT system actually factored (K1: A D A' + Rd, K2: the augmented matrix) in FP64 from A itself, corrected through
+        // the same factor.  Off by default (refine_steps = 0 reproduces the reference's single solve).
+        Scope sc(s, 19);
+        for (int it = 0; it < s->refine; ++it) {
+            CK(cudaMemcpyAsync(s->dc_y, s->ctx.wk, nb, cudaMemcpyDeviceToDevice, s->stream));
+            if (s->system == TLPB200_K1) launch_dc_residual(s->ctx, s->mat, s->d_d, s->d_regD, s->dc_xi, s->dc_y, s->dc_tn, s->stream);
+            else launch_k2_residual(s->ctx, s->mat, s->d_theta, s->d_regP, s->d_regD, s->dc_xi, s->dc_y, s->stream);
+            if (s->ctx.ndblk > 0) CK(cudaMemsetAsync(s->ctx.flags, 0, (size_t)2 * s->ctx.ndblk * sizeof(int32_t), s->stream));
+            enqueue_fwd(s, count);
+            enqueue_bwd(s, count);
+            launch_dc_axpy(s->ctx, s->dc_y, s->stream);
+            count += 4;
+        }
+    }
     if (s->dc.nd > 0) {
         Scope sc(s, 12);
         launch_dc_apply(s->ctx, s->dc, s->stream);
@@ -869,6 +885,13 @@ void setup_device(tlpb200_solver* s) {
         if (const char* e = getenv("TLPB200_DC_REFINE")) s->dc_refine = std::max(0, atoi(e));
     }
 
+    s->refine = (s->nranks == 1) ? std::max(0, std::min(8, (int)s->opt.refine_steps)) : 0;
+    if (const char* e = getenv("TLPB200_REFINE")) s->refine = (s->nranks == 1) ? std::max(0, std::min(8, atoi(e))) : 0;
+    if (s->refine > 0 && s->dense_cols.empty()) {
+        s->dc_xi = dalloc<double>(s, S.N);
+        s->dc_y = dalloc<double>(s, S.N);
+        s->dc_tn = dalloc<double>(s, s->n);
+    }
     s->d_theta = dalloc<double>(s, s->n);
     s->d_regP = dalloc<double>(s, s->n);
     s->d_regD = dalloc<double>(s, s->m);

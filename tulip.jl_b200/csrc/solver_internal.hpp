@@ -106,6 +106,7 @@ struct tlpb200_solver {
     DenseCols dc{};
     double *dc_xi = nullptr, *dc_y = nullptr, *dc_tn = nullptr;   // refinement work vectors
     int dc_refine = 2;
+    int refine = 0;               // general iterative-refinement steps inside solve! (tlpb200_options::refine_steps; 0 = off)
     std::string err;
     tlpb200_ipm* ipm = nullptr;   // device-resident IPM state (tlpb200_hsd_create); owned, freed by tlpb200_destroy
 };

@@ -39,6 +39,7 @@ Base.@kwdef struct Backend <: AbstractKKTBackend
     dense_solve_ncol::Int32 = 0      # supernodes with >= this many columns use the dense-solve sweeps (0 = 384)
     ozaki_ncol::Int32 = 0            # K1: supernodes with >= this many columns run their far Schur updates on the
                                      # tcgen05 int8 tensor-core path (0 = 1024, < 0 = FP64 DMMA path everywhere)
+    refine_steps::Int32 = 0          # iterative-refinement steps inside solve! (0 = the reference's single solve)
 end
 
 # layout must match `tlpb200_options`
@@ -46,8 +47,8 @@ struct COptions
     ordering::Int32; device::Int32; piece_width::Int32; small_elems::Int32
     relax_always::Int32; use_graph::Int32; analyze_only::Int32
     rank::Int32; nranks::Int32; dense_col_threshold::Int32
-    dense_solve_ncol::Int32; ozaki_ncol::Int32
-    reserved::NTuple{4,Int32}
+    dense_solve_ncol::Int32; ozaki_ncol::Int32; refine_steps::Int32
+    reserved::NTuple{3,Int32}
 end
 
 mutable struct B200Solver{S<:AbstractKKTSystem} <: AbstractKKTSolver{Float64}
@@ -60,7 +61,7 @@ mutable struct B200Solver{S<:AbstractKKTSystem} <: AbstractKKTSolver{Float64}
         m, n = size(A)
         opt = Ref(COptions(b.ordering, b.device, b.piece_width, b.small_elems, b.relax_always,
                            b.use_graph ? 1 : 0, 0, 0, 1, b.dense_col_threshold, b.dense_solve_ncol, b.ozaki_ncol,
-                           ntuple(_ -> Int32(0), 4)))
+                           b.refine_steps, ntuple(_ -> Int32(0), 3)))
         h = Ref{Ptr{Cvoid}}(C_NULL)
         rc = ccall((:tlpb200_create, libtlpb200), Cint,
                    (Ref{Ptr{Cvoid}}, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Cint, Cint, Ref{COptions}),

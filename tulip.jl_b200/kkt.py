@@ -51,6 +51,7 @@ class Backend:
     dense_col_threshold: int = 0  # K1 dense-column Schur path: 0 auto (max(32, 5% of m)), < 0 off
     dense_solve_ncol: int = 0     # supernodes with >= this many columns use the dense-solve path (0 = default 384)
     ozaki_ncol: int = 0           # K1: supernodes with >= this many columns use the tcgen05 int8 update path (0 = default 1024, < 0 off)
+    refine_steps: int = 0         # iterative-refinement steps inside solve!; 0 = the reference's single solve
 
 
 # ---- exceptions (what the reference throws at this boundary) ---------------------------------
@@ -117,6 +118,7 @@ class B200KKTSolver:
         opt.dense_col_threshold = backend.dense_col_threshold
         opt.dense_solve_ncol = backend.dense_solve_ncol
         opt.ozaki_ncol = backend.ozaki_ncol
+        opt.refine_steps = backend.refine_steps
         colptr = np.ascontiguousarray(A.indptr, dtype=np.int64)
         rowval = np.ascontiguousarray(A.indices, dtype=np.int64)
         nzval = np.ascontiguousarray(A.data, dtype=np.float64)
