@@ -185,7 +185,12 @@ __global__ void __launch_bounds__(DF_THREADS, 1) k_diag_factor(DevCtx c, int32_t
                         a2 += u[j] * Wp[k2 * LDW + j];
                         a3 += u[j] * Wp[k3 * LDW + j];
                     }
-                    const double c0v = Cs[k * LDD + i], c1v = Cs[k1 * LDD + i], c2v = Cs[k2 * LDD + i], c3v = Cs[k3 * LDD + i];
+                    // every (row i, column) entry has exactly one owner thread; the loads are guarded like the stores so that a
+                    // clamped column index (k1..k3 = w - 1 past the end) never reads an entry its owner is writing (racecheck, r2)
+                    const double c0v = Cs[k * LDD + i];
+                    const double c1v = (k + 4 <= i) ? Cs[(k + 4) * LDD + i] : 0.0;
+                    const double c2v = (k + 8 <= i) ? Cs[(k + 8) * LDD + i] : 0.0;
+                    const double c3v = (k + 12 <= i) ? Cs[(k + 12) * LDD + i] : 0.0;
                     Cs[k * LDD + i] = c0v - a0;
                     if (k + 4 <= i) Cs[(k + 4) * LDD + i] = c1v - a1;
                     if (k + 8 <= i) Cs[(k + 8) * LDD + i] = c2v - a2;
