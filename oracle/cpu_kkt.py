@@ -100,12 +100,15 @@ class CpuSupernodalKKT:
         if rc:
             raise MemoryError("cpu_sn_factor")
 
-    def _fsolve(self, rhs):
-        x = np.ascontiguousarray(rhs[self.perm])
-        rc = self.lib.cpu_sn_solve(C.c_int32(self.N), C.c_int32(self.nsuper), _p(self.sn_first), _p(self.sn_rowptr),
-                                   _p(self.sn_rows), _p(self.sn_xptr), _p(self.sign), _p(self.Lx), _p(x))
+    def _fsolve(self, rhs, mode=0, permuted_in=False, permuted_out=False):
+        """(L S L')^{-1} rhs; mode 1 = L^{-1} only, 2 = L^{-T} S only (vectors then live in permuted numbering)"""
+        x = np.ascontiguousarray(rhs if permuted_in else rhs[self.perm], dtype=np.float64).copy()
+        rc = self.lib.cpu_sn_solve_part(C.c_int32(self.N), C.c_int32(self.nsuper), _p(self.sn_first), _p(self.sn_rowptr),
+                                        _p(self.sn_rows), _p(self.sn_xptr), _p(self.sign), _p(self.Lx), _p(x), C.c_int(mode))
         if rc:
             raise MemoryError("cpu_sn_solve")
+        if permuted_out:
+            return x
         out = np.empty_like(x); out[self.perm] = x
         return out
 

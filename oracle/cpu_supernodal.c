@@ -241,14 +241,21 @@ done:
     return rc;
 }
 
-/* x := (L S L')^{-1} x in permuted numbering */
+/* x := (L S L')^{-1} x in permuted numbering; cpu_sn_solve_part: mode 0 = both sweeps, 1 = x := L^{-1} x only,
+ * 2 = x := L^{-T} S x only (the factorised Schur-complement form of the dense-column tests needs the halves) */
+int cpu_sn_solve_part(int32_t N, int32_t nsuper, const int32_t* sn_first, const int64_t* sn_rowptr,
+                      const int32_t* sn_rows, const int64_t* sn_xptr, const int8_t* sign, const double* Lx, double* x, int mode);
 int cpu_sn_solve(int32_t N, int32_t nsuper, const int32_t* sn_first, const int64_t* sn_rowptr,
                  const int32_t* sn_rows, const int64_t* sn_xptr, const int8_t* sign, const double* Lx, double* x) {
+    return cpu_sn_solve_part(N, nsuper, sn_first, sn_rowptr, sn_rows, sn_xptr, sign, Lx, x, 0);
+}
+int cpu_sn_solve_part(int32_t N, int32_t nsuper, const int32_t* sn_first, const int64_t* sn_rowptr,
+                      const int32_t* sn_rows, const int64_t* sn_xptr, const int8_t* sign, const double* Lx, double* x, int mode) {
     double* w = (double*)malloc(sizeof(double) * (size_t)(N > 0 ? N : 1));
     if (!w) return 2;
     const int ione = 1;
     const double one = 1.0, mone = -1.0, zero = 0.0;
-    for (int32_t s = 0; s < nsuper; ++s) {
+    for (int32_t s = 0; s < nsuper && mode != 2; ++s) {
         const int32_t f = sn_first[s];
         const int ns = sn_first[s + 1] - f;
         const int64_t rp = sn_rowptr[s];
@@ -260,6 +267,7 @@ int cpu_sn_solve(int32_t N, int32_t nsuper, const int32_t* sn_first, const int64
             for (int i = 0; i < nr; ++i) x[sn_rows[rp + ns + i]] -= w[i];
         }
     }
+    if (mode == 1) { free(w); return 0; }
     for (int32_t q = 0; q < N; ++q) if (sign[q] < 0) x[q] = -x[q];
     for (int32_t s = nsuper - 1; s >= 0; --s) {
         const int32_t f = sn_first[s];

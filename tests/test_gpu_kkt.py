@@ -499,3 +499,18 @@ def test_iterative_refinement_option(sysname):
     assert res[1] <= max(2.0 * res[0], 1e-12 * scale), res
     assert res[1] <= SQRT_EPS * scale
     assert np.abs(sols[1] - sols[0]).max() <= 1e-5 * np.abs(sols[0]).max()
+
+
+def test_dense_columns_full_size_ipm_converges():
+    """config 5 at BASELINE size through the whole IPM.  Round-2 regression: with the explicit Sherman-Morrison-Woodbury
+    formula the solves lost all accuracy once the dense columns became basic (K_s singular up to the regularisation) and the
+    IPM stalled at pfeas ~ 5 until the iteration limit; the factorised Schur form converges like the CPU port's K2
+    (`python bench.py --impl reference --config 5`: Trm_Optimal after 17 iterations, objective 50833.48157246)."""
+    lp = lpgen.config(5)
+    k = pkg.setup(lp.A, pkg.K1(), pkg.Backend())
+    assert len(k.dense_cols()) == 8
+    h = hsd.HSD(lp.A, lp.b, lp.c, lp.l, lp.u, k)
+    assert h.optimize() == "Trm_Optimal"
+    assert h.niter <= 20
+    assert abs(h.primal_objective - 50833.48157246) <= 1e-7 * 50833.48157246
+    assert abs(h.primal_objective - h.dual_objective) <= 1e-8 * (1 + abs(h.dual_objective))

@@ -575,14 +575,36 @@ __global__ void k_k1_rhs(DevCtx c, DevMat A, const double* __restrict__ d, const
     c.wk[c.iperm[i]] = v;
 }
 
+// v_j = sum_p A[p, j] y[iperm[row_p]] with one thread per column; a column longer than 64 entries (the dense columns of
+// BASELINE config 5 hold 25 000) is walked by its whole warp instead of one lane (measured: 4.8 ms -> the serial lane was the
+// whole cost of rhs + recovery on config 5).  Every lane of the warp must call this.
+__device__ __forceinline__ double col_dot_perm(const DevMat& A, const int32_t* __restrict__ iperm, const double* __restrict__ y,
+                                               int64_t j, int64_t row_shift) {
+    const int lane = threadIdx.x & 31;
+    const int64_t b = (j < A.n) ? A.colptr[j] : 0, e = (j < A.n) ? A.colptr[j + 1] : 0;
+    const bool is_long = e - b > 64;
+    double v = 0.0;
+    if (!is_long)
+        for (int64_t p = b; p < e; ++p) v += A.val[p] * y[iperm[row_shift + A.rowidx[p]]];
+    unsigned mask = __ballot_sync(0xffffffffu, is_long);
+    while (mask) {
+        const int src = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const int64_t bb = __shfl_sync(0xffffffffu, b, src), ee = __shfl_sync(0xffffffffu, e, src);
+        double a = 0.0;
+        for (int64_t p = bb + lane; p < ee; p += 32) a += A.val[p] * y[iperm[row_shift + A.rowidx[p]]];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == src) v = a;
+    }
+    return v;
+}
+
 __global__ void k_k1_recover(DevCtx c, DevMat A, const double* __restrict__ d, const double* __restrict__ xi_d,
                              double* __restrict__ dx, double* __restrict__ dy) {
     const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (j < A.n) {
-        double v = 0.0;
-        for (int64_t p = A.colptr[j]; p < A.colptr[j + 1]; ++p) v += A.val[p] * c.wk[c.iperm[A.rowidx[p]]];
-        dx[j] = d[j] * (v - xi_d[j]);
-    }
+    const double v = col_dot_perm(A, c.iperm, c.wk, j, 0);
+    if (j < A.n) dx[j] = d[j] * (v - xi_d[j]);
     if (j < A.m) dy[j] = c.wk[c.iperm[j]];
 }
 

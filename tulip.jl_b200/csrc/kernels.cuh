@@ -101,10 +101,14 @@ struct DenseCols {
     const int32_t* prow;     // permuted row index of every entry
     const double* val;
     const int32_t* col_id;   // [nd] original column index
-    double* V;               // [nd][N]   K_s^{-1} A_d, permuted order
-    double* C;               // [nd*nd]   Gram matrix, then its Cholesky factor (row-major lower)
+    double* Wt;              // [nd][N]   forward-swept dense columns as the sweep kernels leave them: G L^{-1} P A_d
+    double* Wh;              // [nd][N]   (G G')^{-1} Wt, so that Wh' Wt = W'W with W = L^{-1} P A_d (see kernels_dense_cols.cu)
+    double* C;               // [nd*nd]   D_d^{-1} + W'W, then its Cholesky factor (row-major lower)
     double* g;               // [nd]
+    const int32_t* gblk;     // [3 * ngblk] {diagonal-block index, first permuted column, width} of the dense-solve supernodes' blocks
+    int32_t ngblk;
 };
+void launch_dc_ginv(const DevCtx& c, const DenseCols& dc, const double* in, double* out, cudaStream_t st);
 void launch_dc_scatter(const DevCtx& c, const DenseCols& dc, int j, int64_t colnnz, cudaStream_t st);
 void launch_dc_gram_chol(const DevCtx& c, const DenseCols& dc, const double* theta, const double* regP, cudaStream_t st);
 void launch_dc_apply(const DevCtx& c, const DenseCols& dc, cudaStream_t st);

@@ -1,12 +1,23 @@
 // Dense-column handling for the normal equations (BASELINE config 5; a capability the reference lacks:
 // with K1 its A*D*A' simply becomes dense, /root/reference/src/KKT/Cholmod/spd.jl:43).
 //
-//   A = [A_s  A_d],  K = A_s D_s A_s' + Rd + A_d D_d A_d' = K_s + A_d D_d A_d'
-// K_s keeps the sparse factorisation; the nd dense columns enter through the Schur complement of the
-// bordered system (Sherman-Morrison-Woodbury):
-//   V = K_s^{-1} A_d               (nd sparse solves per update!)
-//   C = D_d^{-1} + A_d' V          (nd x nd, SPD), C = Lc Lc'
-//   K^{-1} b = y0 - V C^{-1} (A_d' y0),   y0 = K_s^{-1} b
+//   A = [A_s  A_d],  K = A_s D_s A_s' + Rd + A_d D_d A_d' = K_s + A_d D_d A_d',   K_s = L L'
+// K_s keeps the sparse factorisation; the nd dense columns enter through the Schur complement of the bordered system, in
+// FACTORISED form (block elimination of [K_s A_d; A_d' -D_d^{-1}] with the sparse part first):
+//   W = L^{-1} A_d                 (nd forward sweeps per update!)
+//   C = D_d^{-1} + W'W             (nd x nd, a Gram matrix + positive diagonal: SPD by construction), C = Lc Lc'
+//   K^{-1} b = L^{-T} ( z - W C^{-1} W'z ),   z = L^{-1} b
+// Round 1 used the explicit Sherman-Morrison-Woodbury formula y0 - V C^{-1} A_d'y0 with V = K_s^{-1} A_d, y0 = K_s^{-1} b.
+// Near IPM convergence the dense columns are basic and K_s alone is singular up to the regularisation (cond ~ 1e16): both
+// terms of that formula are amplified by 1/lambda_min(K_s) and cancel, and the refinement built on it DIVERGES -- the
+// config-5 IPM stalled at pfeas ~ 5 from iteration 18 on (reproduced with a NumPy emulation on the CPU port's factor;
+// 17 iterations to Trm_Optimal with the factorised form, the same count as the CPU port's K2).  In the factorised form the
+// correction is subtracted half-way, before L^{-T} amplifies anything.
+//
+// The forward-sweep kernels leave the blocks of a dense-solve ("big") supernode scaled by its diagonal blocks
+// (kernels_dense_solve.cu: w = G u, G = blockdiag(L_kk) there, identity elsewhere).  With Wt = G W (what the sweep
+// returns) and Wh = (G G')^{-1} Wt:  W'W = Wh'Wt,  W'z = Wh'(G z),  G (z - W t) = G z - Wt t -- so everything is done on
+// the vectors exactly as the sweeps produce and consume them.
 #include "kernels.cuh"
 
 namespace tlp {
@@ -29,17 +40,41 @@ __global__ void k_dc_scatter(DevCtx c, DenseCols dc, int j) {
     if (p < dc.colptr[j + 1]) c.wk[dc.prow[p]] = dc.val[p];
 }
 
-// C[i][j] = A_d(:,i)' V_j  (+ theta+regP of dense column i on the diagonal = D_d^{-1})
+// C[i][j] = Wh_i' Wt_j  (+ theta+regP of dense column i on the diagonal = D_d^{-1})
 __global__ void k_dc_gram(DevCtx c, DenseCols dc, const double* __restrict__ theta, const double* __restrict__ regP) {
     __shared__ double red[32];
     const int i = blockIdx.x, j = blockIdx.y;
-    const double* Vj = dc.V + (int64_t)j * c.N;
+    const double* Wi = dc.Wh + (int64_t)i * c.N;
+    const double* Wj = dc.Wt + (int64_t)j * c.N;
     double a = 0.0;
-    for (int64_t p = dc.colptr[i] + threadIdx.x; p < dc.colptr[i + 1]; p += blockDim.x) a += dc.val[p] * Vj[dc.prow[p]];
+    for (int32_t q = threadIdx.x; q < c.N; q += blockDim.x) a += Wi[q] * Wj[q];
     a = block_sum(a, red);
     if (threadIdx.x == 0) {
         if (i == j) a += theta[dc.col_id[i]] + regP[dc.col_id[i]];
         dc.C[i * dc.nd + j] = a;
+    }
+}
+
+// out = (G G')^{-1} in on the diagonal blocks of the dense-solve supernodes (G_kk = L_kk): two triangular products with the
+// explicit inverse X = L_kk^{-1} (Dinv: column-major lower, DinvT: its transpose); one CTA per block.  `out` already holds a
+// copy of `in` for all other entries.
+__global__ void __launch_bounds__(SBLK) k_dc_ginv(DevCtx c, DenseCols dc, const double* __restrict__ in, double* __restrict__ out) {
+    __shared__ double xs[SBLK], ys[SBLK];
+    const int32_t d = dc.gblk[3 * blockIdx.x], col0 = dc.gblk[3 * blockIdx.x + 1], w = dc.gblk[3 * blockIdx.x + 2];
+    const double* X = c.Dinv + (int64_t)d * SBLK * SBLK;      // X[r, cc] at cc * SBLK + r
+    const double* XT = c.DinvT + (int64_t)d * SBLK * SBLK;    // X[r, cc] at r * SBLK + cc
+    const int t = threadIdx.x;
+    xs[t] = t < w ? in[col0 + t] : 0.0;
+    __syncthreads();
+    double y = 0.0;
+    if (t < w)
+        for (int cc = 0; cc <= t; ++cc) y += X[cc * SBLK + t] * xs[cc];        // y = L^{-1} x
+    ys[t] = y;
+    __syncthreads();
+    if (t < w) {
+        double z = 0.0;
+        for (int r = t; r < w; ++r) z += XT[r * SBLK + t] * ys[r];             // z = L^{-T} y
+        out[col0 + t] = z;
     }
 }
 
@@ -71,17 +106,18 @@ __global__ void k_dc_chol(DevCtx c, DenseCols dc) {
     }
 }
 
-// g[i] = A_d(:,i)' wk
+// g[i] = Wh_i' wk   (= W_i' z for the forward-swept vector in wk)
 __global__ void k_dc_dots(DevCtx c, DenseCols dc) {
     __shared__ double red[32];
     const int i = blockIdx.x;
+    const double* Wi = dc.Wh + (int64_t)i * c.N;
     double a = 0.0;
-    for (int64_t p = dc.colptr[i] + threadIdx.x; p < dc.colptr[i + 1]; p += blockDim.x) a += dc.val[p] * c.wk[dc.prow[p]];
+    for (int32_t q = threadIdx.x; q < c.N; q += blockDim.x) a += Wi[q] * c.wk[q];
     a = block_sum(a, red);
     if (threadIdx.x == 0) dc.g[i] = a;
 }
 
-// t = C^{-1} g (every block redundantly, nd <= 64), then wk -= sum_i V_i t_i
+// t = C^{-1} g (every block redundantly, nd <= 64), then wk -= sum_i Wt_i t_i
 __global__ void k_dc_apply(DevCtx c, DenseCols dc) {
     __shared__ double t[64];
     const int nd = dc.nd;
@@ -101,7 +137,7 @@ __global__ void k_dc_apply(DevCtx c, DenseCols dc) {
     const int32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= c.N) return;
     double a = 0.0;
-    for (int i = 0; i < nd; ++i) a += dc.V[(int64_t)i * c.N + q] * t[i];
+    for (int i = 0; i < nd; ++i) a += dc.Wt[(int64_t)i * c.N + q] * t[i];
     c.wk[q] -= a;
 }
 
@@ -109,10 +145,25 @@ __global__ void k_dc_apply(DevCtx c, DenseCols dc) {
 // ill-conditioned, which it is near IPM convergence):  r = xi - (A D A' + Rd) y, all in permuted row order
 __global__ void k_dc_at_y(DevCtx c, DevMat A, const double* __restrict__ d, const double* __restrict__ y, double* __restrict__ tn) {
     const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (j >= A.n) return;
+    // one thread per column, a whole warp for a long (dense) column
+    const int lane = threadIdx.x & 31;
+    const int64_t b = (j < A.n) ? A.colptr[j] : 0, e = (j < A.n) ? A.colptr[j + 1] : 0;
+    const bool is_long = e - b > 64;
     double v = 0.0;
-    for (int64_t p = A.colptr[j]; p < A.colptr[j + 1]; ++p) v += A.val[p] * y[c.iperm[A.rowidx[p]]];
-    tn[j] = d[j] * v;
+    if (!is_long)
+        for (int64_t p = b; p < e; ++p) v += A.val[p] * y[c.iperm[A.rowidx[p]]];
+    unsigned mask = __ballot_sync(0xffffffffu, is_long);
+    while (mask) {
+        const int src = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const int64_t bb = __shfl_sync(0xffffffffu, b, src), ee = __shfl_sync(0xffffffffu, e, src);
+        double a = 0.0;
+        for (int64_t p = bb + lane; p < ee; p += 32) a += A.val[p] * y[c.iperm[A.rowidx[p]]];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == src) v = a;
+    }
+    if (j < A.n) tn[j] = d[j] * v;
 }
 __global__ void k_dc_residual(DevCtx c, DevMat A, const double* __restrict__ regD, const double* __restrict__ xi,
                               const double* __restrict__ y, const double* __restrict__ tn) {
@@ -165,6 +216,10 @@ void launch_dc_scatter(const DevCtx& c, const DenseCols& dc, int j, int64_t coln
 void launch_dc_gram_chol(const DevCtx& c, const DenseCols& dc, const double* theta, const double* regP, cudaStream_t st) {
     k_dc_gram<<<dim3(dc.nd, dc.nd), 256, 0, st>>>(c, dc, theta, regP);
     k_dc_chol<<<1, 256, 0, st>>>(c, dc);
+}
+void launch_dc_ginv(const DevCtx& c, const DenseCols& dc, const double* in, double* out, cudaStream_t st) {
+    cudaMemcpyAsync(out, in, (size_t)c.N * 8, cudaMemcpyDeviceToDevice, st);
+    if (dc.ngblk > 0) k_dc_ginv<<<dc.ngblk, SBLK, 0, st>>>(c, dc, in, out);
 }
 void launch_dc_apply(const DevCtx& c, const DenseCols& dc, cudaStream_t st) {
     k_dc_dots<<<dc.nd, 256, 0, st>>>(c, dc);

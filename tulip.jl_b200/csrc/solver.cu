@@ -361,16 +361,17 @@ void enqueue_factor(tlpb200_solver* s, int64_t& count) {
     if ((*s->cur).ndblk > inv_done) { Scope sc(s, 10); launch_invert_diag((*s->cur), inv_done, (*s->cur).ndblk, st); count++; }
     if ((int32_t)s->plan.big_pack.size() > pack_done) { Scope sc(s, 13); launch_pack_big((*s->cur), pack_done, (int32_t)s->plan.big_pack.size(), st); count++; }
     if (s->dc.nd > 0) {
-        // V = K_s^{-1} A_d : one sparse solve per dense column, then the nd x nd Schur matrix and its Cholesky factor
+        // W = L^{-1} A_d : one forward sweep per dense column (kept as the sweeps leave it, plus its (G G')^{-1} image), then
+        // the nd x nd Schur matrix D_d^{-1} + W'W and its Cholesky factor (kernels_dense_cols.cu)
         Scope sc(s, 12);
         for (int j = 0; j < s->dc.nd; ++j) {
             CK(cudaMemsetAsync(s->ctx.wk, 0, (size_t)s->sym.N * 8, st));
             if (s->ctx.ndblk > 0) CK(cudaMemsetAsync(s->ctx.flags, 0, (size_t)2 * s->ctx.ndblk * sizeof(int32_t), st));
             launch_dc_scatter(s->ctx, s->dc, j, s->dc_colptr[j + 1] - s->dc_colptr[j], st);
             enqueue_fwd(s, count);
-            enqueue_bwd(s, count);
-            CK(cudaMemcpyAsync(s->dc.V + (size_t)j * s->sym.N, s->ctx.wk, (size_t)s->sym.N * 8, cudaMemcpyDeviceToDevice, st));
-            count++;
+            CK(cudaMemcpyAsync(s->dc.Wt + (size_t)j * s->sym.N, s->ctx.wk, (size_t)s->sym.N * 8, cudaMemcpyDeviceToDevice, st));
+            launch_dc_ginv(s->ctx, s->dc, s->dc.Wt + (size_t)j * s->sym.N, s->dc.Wh + (size_t)j * s->sym.N, st);
+            count += 3;
         }
         launch_dc_gram_chol(s->ctx, s->dc, s->d_theta, s->d_regP, st);
         count += 2;
@@ -428,6 +429,11 @@ void enqueue_solve(tlpb200_solver* s, const double* xip, const double* xid, doub
     const size_t nb = (size_t)s->sym.N * 8;
     if (s->dc.nd > 0 || s->refine > 0) CK(cudaMemcpyAsync(s->dc_xi, s->ctx.wk, nb, cudaMemcpyDeviceToDevice, s->stream));
     enqueue_fwd(s, count);
+    if (s->dc.nd > 0) {      // Schur correction of the dense columns, half-way between the sweeps
+        Scope sc(s, 12);
+        launch_dc_apply(s->ctx, s->dc, s->stream);
+        count += 2;
+    }
     enqueue_bwd(s, count);
     if (s->dc.nd == 0 && s->refine > 0) {
         // iterative refinement inside solve! (the reference only has TODOs: spd.jl:68, sqd.jl:72): residual of the
@@ -446,17 +452,15 @@ void enqueue_solve(tlpb200_solver* s, const double* xip, const double* xid, doub
         }
     }
     if (s->dc.nd > 0) {
+        // iterative refinement on the full system with the Schur-corrected solve as the preconditioner
         Scope sc(s, 12);
-        launch_dc_apply(s->ctx, s->dc, s->stream);
-        count += 2;
-        // iterative refinement on the full system with the Woodbury solve as the preconditioner
         for (int it = 0; it < s->dc_refine; ++it) {
             CK(cudaMemcpyAsync(s->dc_y, s->ctx.wk, nb, cudaMemcpyDeviceToDevice, s->stream));
             launch_dc_residual(s->ctx, s->mat, s->d_d, s->d_regD, s->dc_xi, s->dc_y, s->dc_tn, s->stream);
             if (s->ctx.ndblk > 0) CK(cudaMemsetAsync(s->ctx.flags, 0, (size_t)2 * s->ctx.ndblk * sizeof(int32_t), s->stream));
             enqueue_fwd(s, count);
-            enqueue_bwd(s, count);
             launch_dc_apply(s->ctx, s->dc, s->stream);
+            enqueue_bwd(s, count);
             launch_dc_axpy(s->ctx, s->dc_y, s->stream);
             count += 5;
         }
@@ -876,7 +880,22 @@ void setup_device(tlpb200_solver* s) {
         s->dc.prow = upload(s, prow);
         s->dc.val = upload(s, dval);
         s->dc.col_id = upload(s, s->dense_cols);
-        s->dc.V = dalloc<double>(s, (size_t)nd * S.N);
+        s->dc.Wt = dalloc<double>(s, (size_t)nd * S.N);
+        s->dc.Wh = dalloc<double>(s, (size_t)nd * S.N);
+        {   // diagonal blocks of the dense-solve supernodes: the forward sweeps leave those entries scaled by L_kk
+            std::vector<int32_t> gb;
+            for (int32_t sn = 0; sn < S.nsuper; ++sn) {
+                if (sn >= (int32_t)P.sn_big.size() || !P.sn_big[sn]) continue;
+                const int32_t f = S.sn_first[sn], nc = S.sn_first[sn + 1] - f;
+                for (int32_t k = 0; k * SBLK < nc; ++k) {
+                    gb.push_back(P.sn_dblk[sn] + k);
+                    gb.push_back(f + k * SBLK);
+                    gb.push_back(std::min<int32_t>(SBLK, nc - k * SBLK));
+                }
+            }
+            s->dc.ngblk = (int32_t)(gb.size() / 3);
+            s->dc.gblk = upload(s, gb);
+        }
         s->dc.C = dalloc<double>(s, (size_t)nd * nd);
         s->dc.g = dalloc<double>(s, nd);
         s->dc_xi = dalloc<double>(s, S.N);
