@@ -55,6 +55,23 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on stdout when the
+# library's communicator is created), so the real stdout is kept aside for the JSON line and fd 1 is pointed at stderr.
+_OUT = None
+
+
+def claim_stdout():
+    global _OUT
+    if _OUT is None:
+        sys.stdout.flush()
+        _OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    print(json.dumps(obj), file=_OUT if _OUT is not None else sys.stdout, flush=True)
+
+
 CONFIGS = {"2": (2, False, "K1"), "3": (3, False, "K2"), "4": (4, False, "K1"), "5": (5, False, "K1"), "T": ("T", False, "K1"),
            "mini": (2, True, "K1"), "3mini": (3, True, "K2"), "4mini": (4, True, "K1"), "5mini": (5, True, "K1"), "Tmini": ("T", True, "K1")}
 
@@ -470,7 +487,7 @@ def gpu_arm(args):
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        emit(out)
 
 
 def sharded_arm(args, cfg, pkg, lp, sysname, sy, dist, rank, world, local):
@@ -539,7 +556,7 @@ def sharded_arm(args, cfg, pkg, lp, sysname, sy, dist, rank, world, local):
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        emit(out)
 
 
 def cpu_sample_extrapolated(st, nsolve, why):
@@ -637,7 +654,7 @@ def reference_arm(args):
             out = dict(base, value=cb["value"], steps=0, warmup=0, ms_per_step=round(1e3 / cb["value"], 1),
                        config={"workload": workload_name(lp, gpu_sysname), "solves_per_step": 5.0}, cpu_baseline=cb,
                        e2e={"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
-            print(json.dumps(out), flush=True)
+            emit(out)
             return
         K, W = 1, 0
     ck = cpu_kkt.CpuSupernodalKKT(A, sysname, nthreads=cores, symbolic_from=an)
@@ -677,7 +694,7 @@ def reference_arm(args):
         json.dump({"host": socket.gethostname(), "when": time.time(), "cpu_baseline": cb, "ipm": ipm}, open(cache_path(cfg), "w"))
     except Exception as e:          # pragma: no cover
         log(f"could not cache the CPU arm's result: {e}")
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def main():
@@ -693,6 +710,7 @@ def main():
                     help="also run the device-resident HSD loop (auto: every config whose factorisation is below 5e12 flops, i.e. not T)")
     ap.add_argument("--no-n1", action="store_true", help="sharded run: skip the single-GPU timing of the same workload on rank 0")
     args = ap.parse_args()
+    claim_stdout()
     if args.warmup < 3 and args.impl == "b200":
         log("note: timing rules ask for >= 3 warm-up steps")
     if args.impl == "reference":
