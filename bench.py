@@ -236,6 +236,21 @@ def record_hsd(pkg, lp, kkt, niter):
     return h, recs
 
 
+def device_ipm_figures(pkg, kkt_local, lp, limit, reduce_max=None):
+    """the whole HSD loop resident on the device (tlpb200_hsd_*): KKT-only event time per iteration and wall clock"""
+    from tulip_jl_b200 import hsd as hsd_mod
+    d = pkg.DeviceHSD(kkt_local, lp.b, lp.c, lp.l, lp.u, params=hsd_mod.IPMOptions(IterationsLimit=limit))
+    d.optimize()                      # warm-up of the IPM kernels
+    d.optimize()
+    kk = d.t_factor + d.t_solve
+    wall = d.info["seconds_total"]
+    if reduce_max is not None:
+        kk, wall = reduce_max([kk, wall])
+    return {"status": d.status, "iters": d.niter, "pobj": d.primal_objective, "dobj": d.dual_objective,
+            "kkt_iter_per_s": round(d.niter / kk, 4) if kk > 0 else None, "kkt_ms_per_iter": round(kk * 1e3 / max(1, d.niter), 4),
+            "whole_ipm_wall_s": round(wall, 4), "whole_ipm_iter_per_s": round(d.niter / wall, 4) if wall > 0 else None}
+
+
 def timed_window(recs, W, K):
     """K records after W warm-up ones; cycles over the post-warm-up iterations when the IPM converged earlier"""
     base = len(recs)
@@ -299,23 +314,14 @@ def gpu_arm(args):
     ipm_dev = None
     if args.ipm_device == "on" or (args.ipm_device == "auto" and st0["flops"] <= ONE_ITER_ABOVE_FLOPS):
         try:
-            from tulip_jl_b200 import hsd as hsd_mod
-            d = pkg.DeviceHSD(kkt, lp.b, lp.c, lp.l, lp.u, params=hsd_mod.IPMOptions(IterationsLimit=max(args.ipm_limit, W + K) if args.ipm_limit > 0 else W + K))
-            d.optimize()                  # warm-up (graph instantiation happened in pass 1; this warms the IPM kernels)
-            d.optimize()
-            kk = d.t_factor + d.t_solve
-            ipm_dev = {"status": d.status, "iters": d.niter, "pobj": d.primal_objective, "dobj": d.dual_objective,
-                       "kkt_iter_per_s": round(d.niter / kk, 4) if kk > 0 else None,
-                       "kkt_ms_per_iter": round(kk * 1e3 / max(1, d.niter), 4),
-                       "whole_ipm_wall_s": round(d.info["seconds_total"], 4),
-                       "whole_ipm_iter_per_s": round(d.niter / d.info["seconds_total"], 4),
-                       "host_mirror_whole_ipm_wall_s": round(h.wall_s, 4),
-                       "host_mirror_whole_ipm_iter_per_s": round(h.niter / h.wall_s, 4),
-                       "pobj_rel_diff_vs_host_mirror": float(abs(d.primal_objective - h.primal_objective) / max(1.0, abs(h.primal_objective))),
-                       "note": "the whole HSD loop (residuals, status tests, theta / rhs / recovery / step-length kernels, update!, solve!) "
-                               "with every vector resident in HBM: per-iteration host traffic = a 312-byte scalar block per decision; "
-                               "kkt_* = CUDA-event time of the update!/solve! sequences only (the metric's numerator), whole_ipm_* = wall "
-                               "clock of the complete solve next to the host-mirror driver's"}
+            ipm_dev = device_ipm_figures(pkg, kkt, lp, max(args.ipm_limit, W + K) if args.ipm_limit > 0 else W + K)
+            ipm_dev.update({"host_mirror_whole_ipm_wall_s": round(h.wall_s, 4),
+                            "host_mirror_whole_ipm_iter_per_s": round(h.niter / h.wall_s, 4),
+                            "pobj_rel_diff_vs_host_mirror": float(abs(ipm_dev["pobj"] - h.primal_objective) / max(1.0, abs(h.primal_objective))),
+                            "note": "the whole HSD loop (residuals, status tests, theta / rhs / recovery / step-length kernels, update!, "
+                                    "solve!) with every vector resident in HBM: per-iteration host traffic = a 312-byte scalar block per "
+                                    "decision; kkt_* = CUDA-event time of the update!/solve! sequences only (the metric's numerator), "
+                                    "whole_ipm_* = wall clock of the complete solve next to the host-mirror driver's"})
         except Exception as e:          # the headline must not depend on the extra measurement
             ipm_dev = {"error": f"{type(e).__name__}: {e}"}
     # ---- pass 2: device-resident replay (value) ---------------------------------------------
@@ -511,6 +517,10 @@ def sharded_arm(args, cfg, pkg, lp, sysname, sy, dist, rank, world, local):
               "update_ms_host_api": round(float(np.mean([r["t_update"] for r in win1[W:W + K]])) * 1e3, 3),
               "solve_ms_host_api": round(float(np.sum([r["t_solve"] for r in win1[W:W + K]]) / np.sum([len(r["rhs"]) for r in win1[W:W + K]])) * 1e3, 3),
               "ipm": ipm_summary(h1), "note": "same workload, same host API, one GPU (rank 0), timed in this run before the sharded solver"}
+        try:
+            n1["ipm_device_resident"] = device_ipm_figures(pkg, k1, lp, limit)
+        except Exception as e:
+            n1["ipm_device_resident"] = {"error": f"{type(e).__name__}: {e}"}
         k1.close()
         del k1, recs1, win1
         torch.cuda.empty_cache()
@@ -553,6 +563,44 @@ def sharded_arm(args, cfg, pkg, lp, sysname, sy, dist, rank, world, local):
            "solve_ms_host_api": round(float(np.sum([r["t_solve"] for r in timed]) / np.sum([len(r["rhs"]) for r in timed])) * 1e3, 3)}
     if n1 is not None:
         out["strong_speedup_vs_n1"] = round(val / n1["value"], 3)
+
+    def reduce_max(v):
+        tt = torch.tensor(v, dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return [float(x) for x in tt]
+
+    # the same sharded solver under the device-resident IPM loop: no host vector work between the KKT calls, so the ranks
+    # stay in lock-step (the host-API figures above include the skew of two Python IPM drivers waiting for each other in NCCL)
+    try:
+        out["ipm_device_resident"] = device_ipm_figures(pkg, kkt.local, lp, limit, reduce_max)
+        if n1 is not None and "kkt_ms_per_iter" in (n1.get("ipm_device_resident") or {}):
+            out["ipm_device_resident"]["strong_speedup_vs_n1"] = round(
+                n1["ipm_device_resident"]["kkt_ms_per_iter"] / out["ipm_device_resident"]["kkt_ms_per_iter"], 3)
+    except Exception as e:
+        out["ipm_device_resident"] = {"error": f"{type(e).__name__}: {e}"}
+    kkt.close()
+    # weak-scaling variant of the same generator: 64 blocks PER RANK (the BASELINE config is the fixed 64-block LP above;
+    # this line shows what the sharding does when the tree has work for every GPU)
+    if not args.no_weak:
+        try:
+            from tulip_jl_b200 import lpgen
+            lpw = lpgen.block_angular(blocks=64 * world, name=f"cfg4_weak_x{world}")
+            kw = parallel.DistB200KKT(lpw.A, sy, pkg.Backend(device=local))
+            dist.barrier()
+            hw, recw = record_hsd(pkg, lpw, kw, W + K)
+            winw, krw = timed_window(recw, W, K)
+            tw = reduce_max([sum(r["t_update"] + r["t_solve"] for r in winw[W:W + K])])[0]
+            stw = kw.stats()
+            out["weak_variant"] = {"workload": workload_name(lpw, sysname), "blocks": 64 * world, "ms_per_step": round(tw * 1e3 / K, 4),
+                                   "value": round(K / tw, 4), "nnzL": stw["nnzL"], "factor_flops": stw["flops"],
+                                   "update_ms_host_api": round(float(np.mean([r["t_update"] for r in winw[W:W + K]])) * 1e3, 3),
+                                   "solve_ms_host_api": round(float(np.sum([r["t_solve"] for r in winw[W:W + K]]) / np.sum([len(r["rhs"]) for r in winw[W:W + K]])) * 1e3, 3),
+                                   "weak_efficiency_vs_n1": round(n1["ms_per_step"] / (tw * 1e3 / K), 3) if n1 is not None else None,
+                                   "note": "per-rank work fixed (64 blocks per GPU + the 512 linking rows), host-pointer API, max over ranks; "
+                                           "efficiency = N=1 ms/step on the 64-block LP / this ms/step"}
+            kw.close()
+        except Exception as e:
+            out["weak_variant"] = {"error": f"{type(e).__name__}: {e}"}
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:
@@ -708,6 +756,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ipm-device", default="auto", choices=["auto", "on", "off"],
                     help="also run the device-resident HSD loop (auto: every config whose factorisation is below 5e12 flops, i.e. not T)")
+    ap.add_argument("--no-weak", action="store_true", help="sharded run: skip the weak-scaling variant (64 blocks per rank)")
     ap.add_argument("--no-n1", action="store_true", help="sharded run: skip the single-GPU timing of the same workload on rank 0")
     args = ap.parse_args()
     claim_stdout()
