@@ -159,6 +159,40 @@ int nccl_fail(tlpb200_solver* s, const NcclFail& f) {
 
 inline bool sharded(const tlpb200_solver* s) { return s->nranks > 1; }
 
+// does [begin, end) of item list `wl` contain anything the current phase processes?  (always, unless a sharded phase is active)
+inline bool has_work(const tlpb200_solver* s, int wl, int64_t begin, int64_t end) {
+    if (end <= begin) return false;
+    const int ph = (s->cur == &s->ctxA) ? 0 : ((s->cur == &s->ctxB) ? 1 : -1);
+    if (ph < 0) return true;
+    const std::vector<int32_t>& pre = s->work_prefix[ph][wl];
+    if (pre.empty()) return true;
+    return pre[(size_t)end] - pre[(size_t)begin] > 0;
+}
+
+void build_work_prefix(tlpb200_solver* s) {
+    const Plan& P = s->plan;
+    for (int ph = 0; ph < 2; ++ph) {
+        auto live = [&](int32_t sn) { return ph == 0 ? (s->owner[sn] == s->rank) : (s->owner[sn] == -1); };
+        auto fill = [&](int wl, size_t n, auto sn_of) {
+            std::vector<int32_t>& pre = s->work_prefix[ph][wl];
+            pre.assign(n + 1, 0);
+            for (size_t i = 0; i < n; ++i) pre[i + 1] = pre[i] + (live(sn_of(i)) ? 1 : 0);
+        };
+        fill(tlpb200_solver::WL_SMALL, P.small_list.size(), [&](size_t i) { return P.small_list[i]; });
+        fill(tlpb200_solver::WL_PIECE, P.level_pieces.size(), [&](size_t i) { return P.pieces[P.level_pieces[i]].sn; });
+        fill(tlpb200_solver::WL_PANEL, P.panel.size(), [&](size_t i) { return P.pieces[P.panel[i].piece].sn; });
+        fill(tlpb200_solver::WL_EXT, P.upd.size(), [&](size_t i) { return P.pieces[P.upd[i].piece].sn; });
+        fill(tlpb200_solver::WL_LAZY, P.upd128.size(), [&](size_t i) { return P.pieces[P.upd128[i].piece].sn; });
+        fill(tlpb200_solver::WL_FWD, P.fwd_items.size(), [&](size_t i) { return P.fwd_items[i].sn; });
+        fill(tlpb200_solver::WL_BWD, P.bwd_items.size(), [&](size_t i) { return P.bwd_items[i].sn; });
+        fill(tlpb200_solver::WL_FBIG, P.fwd_big.size(), [&](size_t i) { return P.fwd_big[i].sn; });
+        fill(tlpb200_solver::WL_BBIG, P.bwd_big.size(), [&](size_t i) { return P.bwd_big[i].sn; });
+        fill(tlpb200_solver::WL_BELOW, P.bwd_below.size(), [&](size_t i) { return P.bwd_below[i].sn; });
+        fill(tlpb200_solver::WL_INV, P.inv_order.size(), [&](size_t i) { return P.dblk_sn[P.inv_order[i]]; });
+        fill(tlpb200_solver::WL_PACK, P.big_pack.size(), [&](size_t i) { return P.big_pack[i].sn; });
+    }
+}
+
 // ---- the numeric phases, enqueued on s->stream; `count` accumulates kernel launches -------------
 void enqueue_assemble(tlpb200_solver* s, int64_t& count) {
     cudaStream_t st = s->stream;
@@ -248,29 +282,29 @@ void enqueue_factor(tlpb200_solver* s, int64_t& count) {
                                      (int32_t)(s->sym.sn_rowptr[v.sn + 1] - s->sym.sn_rowptr[v.sn]), s->oz_E + v.row0, s->oz_scl + v.row0, st);
                     count++;
                 }
-        if (lp.small_end > lp.small_begin) {
+        if (has_work(s, tlpb200_solver::WL_SMALL, lp.small_begin, lp.small_end)) {
             Scope sc(s, 1);
             launch_small_factor((*s->cur), lp.small_begin, lp.small_end, s->small_smem, st);
             count++;
         }
-        if (lp.piece_end > lp.piece_begin) { Scope sc(s, 2); launch_diag_factor((*s->cur), lp.piece_begin, lp.piece_end, st); count++; }
+        if (has_work(s, tlpb200_solver::WL_PIECE, lp.piece_begin, lp.piece_end)) { Scope sc(s, 2); launch_diag_factor((*s->cur), lp.piece_begin, lp.piece_end, st); count++; }
         const bool split = overlap && s->split_chain;
         bool ev_f_recorded = false;
         if (!split) {
-            if (lp.panel_end > lp.panel_begin) { Scope sc(s, 3); launch_trsm((*s->cur), lp.panel_begin, lp.panel_end, st); count++; }
+            if (has_work(s, tlpb200_solver::WL_PANEL, lp.panel_begin, lp.panel_end)) { Scope sc(s, 3); launch_trsm((*s->cur), lp.panel_begin, lp.panel_end, st); count++; }
         } else {
             // Chain (main stream): diagonal blocks -> critical trsm row tiles -> critical update tiles -> next level's
             // diagonal blocks.  The rest of the trsm and of the urgent tiles runs on the aux stream underneath the next
             // diagonal-block factorisation; the next level's trsm joins it.
             CK(cudaEventRecord(s->ev_d[l], st));
             CK(cudaStreamWaitEvent(s->aux_stream, s->ev_d[l], 0));
-            if (lp.panel_end > lp.panel_crit_end) { launch_trsm((*s->cur), lp.panel_crit_end, lp.panel_end, s->aux_stream); count++; }
+            if (has_work(s, tlpb200_solver::WL_PANEL, lp.panel_crit_end, lp.panel_end)) { launch_trsm((*s->cur), lp.panel_crit_end, lp.panel_end, s->aux_stream); count++; }
             CK(cudaEventRecord(s->ev_tr[l], s->aux_stream));
             if (l > 0) CK(cudaStreamWaitEvent(st, s->ev_ur[l - 1], 0));   // rest of the previous level's urgent tiles
-            if (lp.panel_crit_end > lp.panel_begin) { launch_trsm((*s->cur), lp.panel_begin, lp.panel_crit_end, st); count++; }
+            if (has_work(s, tlpb200_solver::WL_PANEL, lp.panel_begin, lp.panel_crit_end)) { launch_trsm((*s->cur), lp.panel_begin, lp.panel_crit_end, st); count++; }
         }
         // the persistent bulk kernel leaves `chain_sms` SMs to the critical-chain kernels
-        if (lp.lazy_end > lp.lazy_begin) {
+        if (has_work(s, tlpb200_solver::WL_LAZY, lp.lazy_begin, lp.lazy_end)) {
             if (!overlap) {
                 Scope sc(s, 8);
                 launch_update_lazy((*s->cur), lp.lazy_begin, lp.lazy_end, s->lazy_ctr + 2 * l, s->nsm, 0, st);
@@ -330,7 +364,7 @@ void enqueue_factor(tlpb200_solver* s, int64_t& count) {
             // a slice of the invert / repack work per level: short-lived CTAs that fill idle SMs of the tail without
             // holding them against the chain kernels
             cudaStream_t ps = s->side2[2];
-            if (!(lp.lazy_end > lp.lazy_begin)) CK(cudaEventRecord(s->ev_f[l], st));
+            if (!has_work(s, tlpb200_solver::WL_LAZY, lp.lazy_begin, lp.lazy_end)) CK(cudaEventRecord(s->ev_f[l], st));
             CK(cudaStreamWaitEvent(ps, s->ev_f[l], 0));
             if (split) CK(cudaStreamWaitEvent(ps, s->ev_tr[l], 0));
             if (lp.inv_end > inv_done) { launch_invert_diag((*s->cur), inv_done, lp.inv_end, ps); inv_done = lp.inv_end; count++; }
@@ -341,13 +375,13 @@ void enqueue_factor(tlpb200_solver* s, int64_t& count) {
             ev_f_recorded = true;
         }
         if (!split) {
-            if (lp.ext_end > lp.ext_begin) { Scope sc(s, 4); launch_update((*s->cur), lp.ext_begin, lp.ext_end, 1, st); count++; }
+            if (has_work(s, tlpb200_solver::WL_EXT, lp.ext_begin, lp.ext_end)) { Scope sc(s, 4); launch_update((*s->cur), lp.ext_begin, lp.ext_end, 1, st); count++; }
         } else {
-            if (!(lp.lazy_end > lp.lazy_begin) && !ev_f_recorded) CK(cudaEventRecord(s->ev_f[l], st));   // critical trsm done
+            if (!has_work(s, tlpb200_solver::WL_LAZY, lp.lazy_begin, lp.lazy_end) && !ev_f_recorded) CK(cudaEventRecord(s->ev_f[l], st));   // critical trsm done
             CK(cudaStreamWaitEvent(s->aux_stream, s->ev_f[l], 0));
-            if (lp.ext_end > lp.ext_crit_end) { launch_update((*s->cur), lp.ext_crit_end, lp.ext_end, 1, s->aux_stream); count++; }
+            if (has_work(s, tlpb200_solver::WL_EXT, lp.ext_crit_end, lp.ext_end)) { launch_update((*s->cur), lp.ext_crit_end, lp.ext_end, 1, s->aux_stream); count++; }
             CK(cudaEventRecord(s->ev_ur[l], s->aux_stream));
-            if (lp.ext_crit_end > lp.ext_begin) { launch_update((*s->cur), lp.ext_begin, lp.ext_crit_end, 1, st); count++; }
+            if (has_work(s, tlpb200_solver::WL_EXT, lp.ext_begin, lp.ext_crit_end)) { launch_update((*s->cur), lp.ext_begin, lp.ext_crit_end, 1, st); count++; }
         }
     }
     if (overlap && s->split_chain && nlev > 0) CK(cudaStreamWaitEvent(st, s->ev_ur[nlev - 1], 0));
@@ -358,8 +392,8 @@ void enqueue_factor(tlpb200_solver* s, int64_t& count) {
         for (long q = oz_waited + 1; q < (long)nlev; ++q)
             if (has_oz[q]) CK(cudaStreamWaitEvent(st, s->ev_oz[q], 0));   // join
     if (early_pack) CK(cudaStreamWaitEvent(st, s->ev_pack, 0));
-    if ((*s->cur).ndblk > inv_done) { Scope sc(s, 10); launch_invert_diag((*s->cur), inv_done, (*s->cur).ndblk, st); count++; }
-    if ((int32_t)s->plan.big_pack.size() > pack_done) { Scope sc(s, 13); launch_pack_big((*s->cur), pack_done, (int32_t)s->plan.big_pack.size(), st); count++; }
+    if (has_work(s, tlpb200_solver::WL_INV, inv_done, (*s->cur).ndblk)) { Scope sc(s, 10); launch_invert_diag((*s->cur), inv_done, (*s->cur).ndblk, st); count++; }
+    if (has_work(s, tlpb200_solver::WL_PACK, pack_done, (int64_t)s->plan.big_pack.size())) { Scope sc(s, 13); launch_pack_big((*s->cur), pack_done, (int32_t)s->plan.big_pack.size(), st); count++; }
     if (s->dc.nd > 0) {
         // W = L^{-1} A_d : one forward sweep per dense column (kept as the sweeps leave it, plus its (G G')^{-1} image), then
         // the nd x nd Schur matrix D_d^{-1} + W'W and its Cholesky factor (kernels_dense_cols.cu)
@@ -395,9 +429,9 @@ void enqueue_fwd(tlpb200_solver* s, int64_t& count) {
     const auto& L = s->plan.levels;
     for (size_t l = 0; l < L.size(); ++l) {
         const LevelPlan& lp = L[l];
-        if (lp.small_end > lp.small_begin) { Scope sc(s, 6); launch_fwd_small((*s->cur), lp.small_begin, lp.small_end, st); count++; }
-        if (lp.fwd_end > lp.fwd_begin) { Scope sc(s, 7); launch_fwd_large((*s->cur), lp.fwd_begin, lp.fwd_end, s->nsm, st); count++; }
-        if (lp.fbig_end > lp.fbig_begin) { Scope sc(s, 14); launch_fwd_big((*s->cur), lp.fbig_begin, lp.fbig_end, s->nsm, st); count++; }
+        if (has_work(s, tlpb200_solver::WL_SMALL, lp.small_begin, lp.small_end)) { Scope sc(s, 6); launch_fwd_small((*s->cur), lp.small_begin, lp.small_end, st); count++; }
+        if (has_work(s, tlpb200_solver::WL_FWD, lp.fwd_begin, lp.fwd_end)) { Scope sc(s, 7); launch_fwd_large((*s->cur), lp.fwd_begin, lp.fwd_end, s->nsm, st); count++; }
+        if (has_work(s, tlpb200_solver::WL_FBIG, lp.fbig_begin, lp.fbig_end)) { Scope sc(s, 14); launch_fwd_big((*s->cur), lp.fbig_begin, lp.fbig_end, s->nsm, st); count++; }
     }
 }
 
@@ -406,10 +440,10 @@ void enqueue_bwd(tlpb200_solver* s, int64_t& count) {
     const auto& L = s->plan.levels;
     for (size_t l = L.size(); l-- > 0;) {
         const LevelPlan& lp = L[l];
-        if (lp.below_end > lp.below_begin) { Scope sc(s, 9); launch_bwd_below((*s->cur), lp.below_begin, lp.below_end, st); count++; }
-        if (lp.bbig_end > lp.bbig_begin) { Scope sc(s, 15); launch_bwd_big((*s->cur), lp.bbig_begin, lp.bbig_end, s->nsm, st); count++; }
-        if (lp.bwd_end > lp.bwd_begin) { Scope sc(s, 9); launch_bwd_large((*s->cur), lp.bwd_begin, lp.bwd_end, s->nsm, st); count++; }
-        if (lp.small_end > lp.small_begin) { Scope sc(s, 11); launch_bwd_small((*s->cur), lp.small_begin, lp.small_end, st); count++; }
+        if (has_work(s, tlpb200_solver::WL_BELOW, lp.below_begin, lp.below_end)) { Scope sc(s, 9); launch_bwd_below((*s->cur), lp.below_begin, lp.below_end, st); count++; }
+        if (has_work(s, tlpb200_solver::WL_BBIG, lp.bbig_begin, lp.bbig_end)) { Scope sc(s, 15); launch_bwd_big((*s->cur), lp.bbig_begin, lp.bbig_end, s->nsm, st); count++; }
+        if (has_work(s, tlpb200_solver::WL_BWD, lp.bwd_begin, lp.bwd_end)) { Scope sc(s, 9); launch_bwd_large((*s->cur), lp.bwd_begin, lp.bwd_end, s->nsm, st); count++; }
+        if (has_work(s, tlpb200_solver::WL_SMALL, lp.small_begin, lp.small_end)) { Scope sc(s, 11); launch_bwd_small((*s->cur), lp.small_begin, lp.small_end, st); count++; }
     }
 }
 
@@ -1054,6 +1088,7 @@ int tlpb200_create(tlpb200_solver** out, int64_t m, int64_t n, const int64_t* co
         if (const char* e = getenv("TLPB200_OZAKI_TILE")) po.oz_tile_n = atoi(e) == 128 ? 128 : (atoi(e) == 64 ? 64 : 0);
         if (const char* e = getenv("TLPB200_OZAKI_KSPLIT")) po.oz_ksplit = std::max(32, (atoi(e) / 32) * 32);
         build_plan(s->sym, po, s->plan);
+        if (s->nranks > 1) build_work_prefix(s);
         lap("build_plan");
         if (system == TLPB200_K1)
             build_assembly_k1(s->sym, m, n, cp_f, ri_f, va_f, s->maps);
