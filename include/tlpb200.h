@@ -169,6 +169,14 @@ int tlpb200_debug_ozaki(const double* P, int64_t R, int64_t K, double* C, int32_
 int tlpb200_debug_update_plan(const tlpb200_solver* s, int64_t* counts, int32_t* upd, int32_t* upd128, int32_t* oz, int32_t* pieces,
                               int32_t* views, int32_t* panel, int32_t* levels, int32_t* small_list, int32_t* level_pieces);
 int tlpb200_debug_big_plan(const tlpb200_solver* s, int64_t* counts, void* pack, void* fwd, void* bwd);
+/* Launch sequences of the triangular sweeps (host data, also on analyze_only handles): the block-solve items of consecutive
+ * levels share one launch and synchronise through per-supernode counters.  counts[4] = #fwd ops, #bwd ops, #fwd items,
+ * #bwd items; ops = int32 records {kind (0 small, 1 merged block-solve, 2 dense-solve, 3 below), begin, end, level};
+ * fwd_need / fwd_parent / bwd_wait / bwd_nitems / sn_parent = per-supernode int32 arrays; items = 24-byte records
+ * {sn, blk, kind, r0, nr, pad} in the order the sweeps walk them.  NULL pointers are skipped. */
+int tlpb200_debug_solve_ops(const tlpb200_solver* s, int64_t* counts, int32_t* fwd_ops, int32_t* bwd_ops, int32_t* fwd_need,
+                            int32_t* fwd_parent, int32_t* bwd_wait, int32_t* bwd_nitems, void* fwd_items, void* bwd_seq,
+                            int32_t* sn_parent);
 
 /* ---- multi-GPU, one process per GPU (no counterpart in the reference, NEWS.md:31) -------------
  * Created with opt.nranks > 1 every rank analyses the same matrix, owns the elimination-tree subtrees

@@ -317,7 +317,18 @@ __device__ __forceinline__ void wait_flag(const int32_t* flag, int32_t* info) {
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(SL_THREADS, 1) k_fwd_large(DevCtx c, int32_t begin, int32_t end) {
+// bounded wait until *cnt >= need (merged-level sweeps: "all items of my in-launch children / parent have finished")
+__device__ __forceinline__ void wait_count(const int32_t* cnt, int32_t need, int32_t* info) {
+    if (threadIdx.x == 0) {
+        int spins = 0;
+        while (ld_acquire(cnt) < need) {
+            if (++spins > (1 << 22)) { atomicExch(info + 2, 1); break; }
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(SL_THREADS, 1) k_fwd_large(DevCtx c, int32_t begin, int32_t end, int merged) {
     extern __shared__ double smem_d[];
     double* Ds = smem_d;                   // [SBLK*SBLK] explicit inverse of the item's diagonal block
     double* xs = Ds + SBLK * SBLK;         // [SBLK]
@@ -345,6 +356,9 @@ __global__ void __launch_bounds__(SL_THREADS, 1) k_fwd_large(DevCtx c, int32_t b
         }
         double t[32];
         double acc = 0.0;
+        // merged levels: the right-hand side of this supernode's columns is final once every item of its children inside
+        // this launch has finished (children outside the launch finished before it started)
+        if (merged && I.kind == 0 && c.fwd_need[s] > 0) wait_count(c.dep_cnt + s, c.fwd_need[s], c.info);
         const double bown = (I.kind == 0 && tid < SBLK && rvalid) ? __ldcg(c.wk + f + I.r0 + tid) : 0.0;   // off the chain
         auto load_tile = [&](int j) {
             const int32_t nbj = min(SBLK, nc - j * SBLK);
@@ -369,6 +383,11 @@ __global__ void __launch_bounds__(SL_THREADS, 1) k_fwd_large(DevCtx c, int32_t b
                 const double v = red[r] + red[SBLK + r] + red[2 * SBLK + r] + red[3 * SBLK + r];
                 atomicAdd(c.wk + c.sn_rows[rp + I.r0 + r], v);
             }
+            if (merged && c.fwd_parent[s] >= 0) {      // publish: this item's contributions are in place
+                __threadfence();
+                __syncthreads();
+                if (tid == 0) atomicAdd(c.dep_cnt + c.fwd_parent[s], 1);
+            }
             __syncthreads();
             continue;
         }
@@ -386,11 +405,14 @@ __global__ void __launch_bounds__(SL_THREADS, 1) k_fwd_large(DevCtx c, int32_t b
             __stcg(c.wk + f + I.r0 + tid, red[tid] + red[SBLK + tid] + red[2 * SBLK + tid] + red[3 * SBLK + tid]);
         __threadfence();
         __syncthreads();
-        if (tid == 0) st_release(fflag + db + I.blk, 1);
+        if (tid == 0) {
+            st_release(fflag + db + I.blk, 1);
+            if (merged && c.fwd_parent[s] >= 0) atomicAdd(c.dep_cnt + c.fwd_parent[s], 1);
+        }
     }
 }
 
-__global__ void __launch_bounds__(SL_THREADS, 1) k_bwd_large(DevCtx c, int32_t begin, int32_t end) {
+__global__ void __launch_bounds__(SL_THREADS, 1) k_bwd_large(DevCtx c, int32_t begin, int32_t end, int merged) {
     extern __shared__ double smem_d[];
     double* Ds = smem_d;                   // [SBLK*SBLK] transposed inverse of the item's diagonal block
     double* xs = Ds + SBLK * SBLK;         // [SBLK]
@@ -398,9 +420,11 @@ __global__ void __launch_bounds__(SL_THREADS, 1) k_bwd_large(DevCtx c, int32_t b
     const int tid = threadIdx.x, r = tid & (SBLK - 1), cg = tid >> 7, lane = tid & 31, wq = (tid >> 5) & 3;
     int32_t* bflag = c.flags + c.ndblk;
     for (int32_t it = begin + blockIdx.x; it < end; it += gridDim.x) {
-        const SolveItem I = c.bwd_items[it];
+        const SolveItem I = merged ? c.bwd_seq[it] : c.bwd_items[it];
         const int32_t s = I.sn;
         if (c.skip && c.skip[s]) continue;
+        // merged levels: x of every ancestor is final once all items of the in-launch parent have finished
+        if (merged && c.bwd_wait[s] >= 0) wait_count(c.dep_cnt + c.nsuper + c.bwd_wait[s], c.bwd_nitems[c.bwd_wait[s]], c.info);
         const int32_t f = c.sn_first[s];
         const int32_t nc = c.sn_first[s + 1] - f;
         const int64_t rp = c.sn_rowptr[s];
@@ -504,7 +528,10 @@ __global__ void __launch_bounds__(SL_THREADS, 1) k_bwd_large(DevCtx c, int32_t b
             __stcg(c.wk + f + i * SBLK + tid, red[tid] + red[SBLK + tid] + red[2 * SBLK + tid] + red[3 * SBLK + tid]);
         __threadfence();
         __syncthreads();
-        if (tid == 0) st_release(bflag + db + i, 1);
+        if (tid == 0) {
+            st_release(bflag + db + i, 1);
+            if (merged) atomicAdd(c.dep_cnt + c.nsuper + s, 1);
+        }
     }
 }
 
@@ -699,11 +726,11 @@ void launch_fwd_small(const DevCtx& c, int32_t begin, int32_t end, cudaStream_t 
 void launch_bwd_small(const DevCtx& c, int32_t begin, int32_t end, cudaStream_t st) {
     if (end > begin) k_bwd_small<<<nblk(end - begin, SOLVE_SMALL_WARPS), 32 * SOLVE_SMALL_WARPS, 0, st>>>(c, begin, end);
 }
-void launch_fwd_large(const DevCtx& c, int32_t begin, int32_t end, int nsm, cudaStream_t st) {
-    if (end > begin) k_fwd_large<<<min(end - begin, nsm), SL_THREADS, SL_SMEM, st>>>(c, begin, end);
+void launch_fwd_large(const DevCtx& c, int32_t begin, int32_t end, int nsm, int merged, cudaStream_t st) {
+    if (end > begin) k_fwd_large<<<min(end - begin, nsm), SL_THREADS, SL_SMEM, st>>>(c, begin, end, merged);
 }
-void launch_bwd_large(const DevCtx& c, int32_t begin, int32_t end, int nsm, cudaStream_t st) {
-    if (end > begin) k_bwd_large<<<min(end - begin, nsm), SL_THREADS, SL_SMEM, st>>>(c, begin, end);
+void launch_bwd_large(const DevCtx& c, int32_t begin, int32_t end, int nsm, int merged, cudaStream_t st) {
+    if (end > begin) k_bwd_large<<<min(end - begin, nsm), SL_THREADS, SL_SMEM, st>>>(c, begin, end, merged);
 }
 void launch_bwd_below(const DevCtx& c, int32_t begin, int32_t end, cudaStream_t st) {
     if (end > begin) k_bwd_below<<<(unsigned)(end - begin), SL_THREADS, 0, st>>>(c, begin);

@@ -61,6 +61,14 @@ struct DevCtx {
     const BelowItem* bwd_below;
     const int32_t* sn_split;       // [nsuper] 1 = rows below the columns are accumulated into bacc by k_bwd_below
     double* bacc;                  // [N] backward accumulator sum_rows L[row, c] x[row]; consumers re-zero their entries
+    // merged-level sweeps (Plan::SolveOp): per-supernode dependency counters and their static targets
+    int32_t* dep_cnt;              // [2 * nsuper] forward: finished items of in-launch children / backward: finished items; zeroed per solve
+    const int32_t* fwd_need;       // [nsuper]
+    const int32_t* fwd_parent;     // [nsuper]
+    const int32_t* bwd_wait;       // [nsuper]
+    const int32_t* bwd_nitems;     // [nsuper]
+    const SolveItem* bwd_seq;      // backward items, levels descending
+    int32_t nsuper;
     const int8_t* skip;   // multi-GPU: skip[s] != 0 -> supernode s is not processed in this phase on this rank (nullptr: none)
 };
 
@@ -133,8 +141,10 @@ void launch_invert_diag(const DevCtx& c, int32_t begin, int32_t end, cudaStream_
 
 void launch_fwd_small(const DevCtx& c, int32_t begin, int32_t end, cudaStream_t st);
 void launch_bwd_small(const DevCtx& c, int32_t begin, int32_t end, cudaStream_t st);
-void launch_fwd_large(const DevCtx& c, int32_t begin, int32_t end, int nsm, cudaStream_t st);
-void launch_bwd_large(const DevCtx& c, int32_t begin, int32_t end, int nsm, cudaStream_t st);
+// merged = 1: [begin, end) spans several levels of fwd_items / bwd_seq and the items synchronise through the dependency
+// counters; merged = 0: one level of fwd_items / bwd_items (the kernel boundary is the synchronisation; sharded phases)
+void launch_fwd_large(const DevCtx& c, int32_t begin, int32_t end, int nsm, int merged, cudaStream_t st);
+void launch_bwd_large(const DevCtx& c, int32_t begin, int32_t end, int nsm, int merged, cudaStream_t st);
 void launch_bwd_below(const DevCtx& c, int32_t begin, int32_t end, cudaStream_t st);
 
 void launch_pack_big(const DevCtx& c, int32_t begin, int32_t end, cudaStream_t st);

@@ -497,6 +497,73 @@ void build_plan(const Symbolic& S, const PlanOptions& opt, Plan& P) {
         lp.below_end = (int32_t)P.bwd_below.size();
     }
 
+    // ---- launch sequences of the triangular sweeps with the block-solve items of consecutive levels merged (SolveOp) ----
+    {
+        const int32_t nlev = (int32_t)P.levels.size();
+        P.fwd_ops.clear(); P.bwd_ops.clear(); P.bwd_seq.clear();
+        P.fwd_need.assign(S.nsuper, 0); P.fwd_parent.assign(S.nsuper, -1);
+        P.bwd_wait.assign(S.nsuper, -1); P.bwd_nitems.assign(S.nsuper, 0);
+        std::vector<int32_t> frun(S.nsuper, -1), brun(S.nsuper, -1), fitems(S.nsuper, 0);
+        // forward: levels ascending; per level the launch order is small, large, big
+        int32_t pend_b = -1, pend_e = -1, pend_l = 0;
+        auto flush_f = [&]() {
+            if (pend_b >= 0 && pend_e > pend_b) P.fwd_ops.push_back(SolveOp{1, pend_b, pend_e, pend_l});
+            pend_b = pend_e = -1;
+        };
+        for (int32_t L = 0; L < nlev; ++L) {
+            const LevelPlan& lp = P.levels[L];
+            if (lp.small_end > lp.small_begin) { flush_f(); P.fwd_ops.push_back(SolveOp{0, lp.small_begin, lp.small_end, L}); }
+            if (lp.fwd_end > lp.fwd_begin) {
+                if (pend_b >= 0 && pend_e != lp.fwd_begin) flush_f();
+                if (pend_b < 0) { pend_b = lp.fwd_begin; pend_l = L; }
+                pend_e = lp.fwd_end;
+                for (int32_t x = lp.fwd_begin; x < lp.fwd_end; ++x) {
+                    frun[P.fwd_items[x].sn] = (int32_t)P.fwd_ops.size();     // id of the op this run will become
+                    fitems[P.fwd_items[x].sn]++;
+                }
+            }
+            if (lp.fbig_end > lp.fbig_begin) { flush_f(); P.fwd_ops.push_back(SolveOp{2, lp.fbig_begin, lp.fbig_end, L}); }
+        }
+        flush_f();
+        for (int32_t s2 = 0; s2 < S.nsuper; ++s2) {
+            const int32_t par = S.sn_parent[s2];
+            if (frun[s2] >= 0 && par >= 0 && frun[par] == frun[s2]) {
+                P.fwd_parent[s2] = par;
+                P.fwd_need[par] += fitems[s2];
+            }
+        }
+        // backward: levels descending; per level the launch order is below, big, large, small
+        std::vector<int32_t> seq_b(nlev, 0), seq_e(nlev, 0);
+        for (int32_t L = nlev - 1; L >= 0; --L) {
+            const LevelPlan& lp = P.levels[L];
+            seq_b[L] = (int32_t)P.bwd_seq.size();
+            for (int32_t x = lp.bwd_begin; x < lp.bwd_end; ++x) { P.bwd_seq.push_back(P.bwd_items[x]); P.bwd_nitems[P.bwd_items[x].sn]++; }
+            seq_e[L] = (int32_t)P.bwd_seq.size();
+        }
+        pend_b = pend_e = -1;
+        auto flush_b = [&]() {
+            if (pend_b >= 0 && pend_e > pend_b) P.bwd_ops.push_back(SolveOp{1, pend_b, pend_e, pend_l});
+            pend_b = pend_e = -1;
+        };
+        for (int32_t L = nlev - 1; L >= 0; --L) {
+            const LevelPlan& lp = P.levels[L];
+            if (lp.below_end > lp.below_begin) { flush_b(); P.bwd_ops.push_back(SolveOp{3, lp.below_begin, lp.below_end, L}); }
+            if (lp.bbig_end > lp.bbig_begin) { flush_b(); P.bwd_ops.push_back(SolveOp{2, lp.bbig_begin, lp.bbig_end, L}); }
+            if (seq_e[L] > seq_b[L]) {
+                if (pend_b >= 0 && pend_e != seq_b[L]) flush_b();
+                if (pend_b < 0) { pend_b = seq_b[L]; pend_l = L; }
+                pend_e = seq_e[L];
+                for (int32_t x = seq_b[L]; x < seq_e[L]; ++x) brun[P.bwd_seq[x].sn] = (int32_t)P.bwd_ops.size();
+            }
+            if (lp.small_end > lp.small_begin) { flush_b(); P.bwd_ops.push_back(SolveOp{0, lp.small_begin, lp.small_end, L}); }
+        }
+        flush_b();
+        for (int32_t s2 = 0; s2 < S.nsuper; ++s2) {
+            const int32_t par = S.sn_parent[s2];
+            if (brun[s2] >= 0 && par >= 0 && brun[par] == brun[s2]) P.bwd_wait[s2] = par;
+        }
+    }
+
     // diagonal blocks and pack tiles in level order: solver.cu starts inverting / repacking the columns that are
     // final while the tail of the factorisation (which leaves most SMs idle) is still running
     P.inv_order.resize(P.pieces.size());

@@ -139,8 +139,24 @@ struct LevelPlan {
     int32_t pack_end = 0;                      // Plan::big_pack[0, pack_end): tiles whose column block is at a level <= this one
 };
 
+// One launch of a triangular sweep (single-GPU path).  The block-solve items of consecutive levels that are not separated
+// by a launch of another kind are merged into ONE persistent launch: inside it a supernode's items wait on counters instead
+// of on a kernel boundary (forward: all items of its in-launch children have finished; backward: all items of its in-launch
+// parent have finished), so a chain of L levels costs L flag hand-overs instead of L launches.
+struct SolveOp {
+    int32_t kind;          // 0 small, 1 large (merged), 2 big, 3 below
+    int32_t begin, end;    // range in small_list / fwd_items or bwd_seq / fwd_big or bwd_big / bwd_below
+    int32_t level;         // level of the op (first level of a merged run)
+};
+
 struct Plan {
     PlanOptions opt;
+    std::vector<SolveOp> fwd_ops, bwd_ops;   // launch sequences of the forward / backward sweep
+    std::vector<SolveItem> bwd_seq;          // bwd_items re-ordered: levels descending (the order the backward sweep walks them)
+    std::vector<int32_t> fwd_need;           // [nsuper] forward: items of in-launch children that must finish first
+    std::vector<int32_t> fwd_parent;         // [nsuper] forward: in-launch parent to notify (-1: none)
+    std::vector<int32_t> bwd_wait;           // [nsuper] backward: in-launch parent to wait for (-1: none)
+    std::vector<int32_t> bwd_nitems;         // [nsuper] backward items of the supernode (= its column blocks)
     std::vector<Piece> pieces;
     std::vector<int32_t> sn_small;        // [nsuper] 1 = handled by the one-CTA kernels
     std::vector<int32_t> sn_level;        // [nsuper] level of the supernode's last item

@@ -223,6 +223,7 @@ void enqueue_assemble(tlpb200_solver* s, int64_t& count) {
 // Profiling mode and TLPB200_NO_OVERLAP=1 use the single-stream order.
 void enqueue_fwd(tlpb200_solver* s, int64_t& count);
 void enqueue_bwd(tlpb200_solver* s, int64_t& count);
+void reset_sweep_state(tlpb200_solver* s, cudaStream_t st);
 
 void enqueue_factor(tlpb200_solver* s, int64_t& count) {
     cudaStream_t st = s->stream;
@@ -400,7 +401,7 @@ void enqueue_factor(tlpb200_solver* s, int64_t& count) {
         Scope sc(s, 12);
         for (int j = 0; j < s->dc.nd; ++j) {
             CK(cudaMemsetAsync(s->ctx.wk, 0, (size_t)s->sym.N * 8, st));
-            if (s->ctx.ndblk > 0) CK(cudaMemsetAsync(s->ctx.flags, 0, (size_t)2 * s->ctx.ndblk * sizeof(int32_t), st));
+            reset_sweep_state(s, st);
             launch_dc_scatter(s->ctx, s->dc, j, s->dc_colptr[j + 1] - s->dc_colptr[j], st);
             enqueue_fwd(s, count);
             CK(cudaMemcpyAsync(s->dc.Wt + (size_t)j * s->sym.N, s->ctx.wk, (size_t)s->sym.N * 8, cudaMemcpyDeviceToDevice, st));
@@ -413,6 +414,13 @@ void enqueue_factor(tlpb200_solver* s, int64_t& count) {
     CK(cudaGetLastError());
 }
 
+// hand-over state of one forward + backward sweep: "block solved" flags and the dependency counters of the merged levels
+// (allocated back to back: flags [2 * ndblk], then dep_cnt [2 * nsuper])
+void reset_sweep_state(tlpb200_solver* s, cudaStream_t st) {
+    const size_t n = (size_t)2 * s->ctx.ndblk + (size_t)2 * s->sym.nsuper;
+    if (n > 0) CK(cudaMemsetAsync(s->ctx.flags, 0, n * sizeof(int32_t), st));
+}
+
 void enqueue_rhs(tlpb200_solver* s, const double* xip, const double* xid, int64_t& count) {
     cudaStream_t st = s->stream;
     {
@@ -421,28 +429,48 @@ void enqueue_rhs(tlpb200_solver* s, const double* xip, const double* xid, int64_
         else launch_k2_rhs((*s->cur), s->mat, xip, xid, st);
     }
     count++;
-    if ((*s->cur).ndblk > 0) CK(cudaMemsetAsync((*s->cur).flags, 0, (size_t)2 * (*s->cur).ndblk * sizeof(int32_t), st));
+    reset_sweep_state(s, st);
 }
 
 void enqueue_fwd(tlpb200_solver* s, int64_t& count) {
     cudaStream_t st = s->stream;
+    if (s->cur == &s->ctx && s->merge_levels) {
+        // single GPU: the plan's launch sequence with the block-solve items of consecutive levels merged (Plan::SolveOp)
+        for (const SolveOp& op : s->plan.fwd_ops) {
+            if (op.kind == 0) { Scope sc(s, 6); launch_fwd_small(s->ctx, op.begin, op.end, st); }
+            else if (op.kind == 1) { Scope sc(s, 7); launch_fwd_large(s->ctx, op.begin, op.end, s->nsm, 1, st); }
+            else { Scope sc(s, 14); launch_fwd_big(s->ctx, op.begin, op.end, s->nsm, st); }
+            count++;
+        }
+        return;
+    }
     const auto& L = s->plan.levels;
     for (size_t l = 0; l < L.size(); ++l) {
         const LevelPlan& lp = L[l];
         if (has_work(s, tlpb200_solver::WL_SMALL, lp.small_begin, lp.small_end)) { Scope sc(s, 6); launch_fwd_small((*s->cur), lp.small_begin, lp.small_end, st); count++; }
-        if (has_work(s, tlpb200_solver::WL_FWD, lp.fwd_begin, lp.fwd_end)) { Scope sc(s, 7); launch_fwd_large((*s->cur), lp.fwd_begin, lp.fwd_end, s->nsm, st); count++; }
+        if (has_work(s, tlpb200_solver::WL_FWD, lp.fwd_begin, lp.fwd_end)) { Scope sc(s, 7); launch_fwd_large((*s->cur), lp.fwd_begin, lp.fwd_end, s->nsm, 0, st); count++; }
         if (has_work(s, tlpb200_solver::WL_FBIG, lp.fbig_begin, lp.fbig_end)) { Scope sc(s, 14); launch_fwd_big((*s->cur), lp.fbig_begin, lp.fbig_end, s->nsm, st); count++; }
     }
 }
 
 void enqueue_bwd(tlpb200_solver* s, int64_t& count) {
     cudaStream_t st = s->stream;
+    if (s->cur == &s->ctx && s->merge_levels) {
+        for (const SolveOp& op : s->plan.bwd_ops) {
+            if (op.kind == 3) { Scope sc(s, 9); launch_bwd_below(s->ctx, op.begin, op.end, st); }
+            else if (op.kind == 2) { Scope sc(s, 15); launch_bwd_big(s->ctx, op.begin, op.end, s->nsm, st); }
+            else if (op.kind == 1) { Scope sc(s, 9); launch_bwd_large(s->ctx, op.begin, op.end, s->nsm, 1, st); }
+            else { Scope sc(s, 11); launch_bwd_small(s->ctx, op.begin, op.end, st); }
+            count++;
+        }
+        return;
+    }
     const auto& L = s->plan.levels;
     for (size_t l = L.size(); l-- > 0;) {
         const LevelPlan& lp = L[l];
         if (has_work(s, tlpb200_solver::WL_BELOW, lp.below_begin, lp.below_end)) { Scope sc(s, 9); launch_bwd_below((*s->cur), lp.below_begin, lp.below_end, st); count++; }
         if (has_work(s, tlpb200_solver::WL_BBIG, lp.bbig_begin, lp.bbig_end)) { Scope sc(s, 15); launch_bwd_big((*s->cur), lp.bbig_begin, lp.bbig_end, s->nsm, st); count++; }
-        if (has_work(s, tlpb200_solver::WL_BWD, lp.bwd_begin, lp.bwd_end)) { Scope sc(s, 9); launch_bwd_large((*s->cur), lp.bwd_begin, lp.bwd_end, s->nsm, st); count++; }
+        if (has_work(s, tlpb200_solver::WL_BWD, lp.bwd_begin, lp.bwd_end)) { Scope sc(s, 9); launch_bwd_large((*s->cur), lp.bwd_begin, lp.bwd_end, s->nsm, 0, st); count++; }
         if (has_work(s, tlpb200_solver::WL_SMALL, lp.small_begin, lp.small_end)) { Scope sc(s, 11); launch_bwd_small((*s->cur), lp.small_begin, lp.small_end, st); count++; }
     }
 }
@@ -478,7 +506,7 @@ void enqueue_solve(tlpb200_solver* s, const double* xip, const double* xid, doub
             CK(cudaMemcpyAsync(s->dc_y, s->ctx.wk, nb, cudaMemcpyDeviceToDevice, s->stream));
             if (s->system == TLPB200_K1) launch_dc_residual(s->ctx, s->mat, s->d_d, s->d_regD, s->dc_xi, s->dc_y, s->dc_tn, s->stream);
             else launch_k2_residual(s->ctx, s->mat, s->d_theta, s->d_regP, s->d_regD, s->dc_xi, s->dc_y, s->stream);
-            if (s->ctx.ndblk > 0) CK(cudaMemsetAsync(s->ctx.flags, 0, (size_t)2 * s->ctx.ndblk * sizeof(int32_t), s->stream));
+            reset_sweep_state(s, s->stream);
             enqueue_fwd(s, count);
             enqueue_bwd(s, count);
             launch_dc_axpy(s->ctx, s->dc_y, s->stream);
@@ -491,7 +519,7 @@ void enqueue_solve(tlpb200_solver* s, const double* xip, const double* xid, doub
         for (int it = 0; it < s->dc_refine; ++it) {
             CK(cudaMemcpyAsync(s->dc_y, s->ctx.wk, nb, cudaMemcpyDeviceToDevice, s->stream));
             launch_dc_residual(s->ctx, s->mat, s->d_d, s->d_regD, s->dc_xi, s->dc_y, s->dc_tn, s->stream);
-            if (s->ctx.ndblk > 0) CK(cudaMemsetAsync(s->ctx.flags, 0, (size_t)2 * s->ctx.ndblk * sizeof(int32_t), s->stream));
+            reset_sweep_state(s, s->stream);
             enqueue_fwd(s, count);
             launch_dc_apply(s->ctx, s->dc, s->stream);
             enqueue_bwd(s, count);
@@ -786,7 +814,16 @@ void setup_device(tlpb200_solver* s) {
     c.Dinv = dalloc<double>(s, (size_t)P.ndblk * SBLK * SBLK);
     c.DinvT = dalloc<double>(s, (size_t)P.ndblk * SBLK * SBLK);
     c.LsubT = dalloc<double>(s, (size_t)P.ndblk * SBLK * SBLK);
-    c.flags = dalloc<int32_t>(s, (size_t)2 * P.ndblk);
+    c.flags = dalloc<int32_t>(s, (size_t)2 * P.ndblk + (size_t)2 * S.nsuper);
+    CK(cudaMemset(c.flags, 0, std::max<size_t>((size_t)2 * P.ndblk + (size_t)2 * S.nsuper, 1) * sizeof(int32_t)));
+    c.dep_cnt = c.flags + (size_t)2 * P.ndblk;
+    c.fwd_need = upload(s, P.fwd_need);
+    c.fwd_parent = upload(s, P.fwd_parent);
+    c.bwd_wait = upload(s, P.bwd_wait);
+    c.bwd_nitems = upload(s, P.bwd_nitems);
+    c.bwd_seq = upload(s, P.bwd_seq);
+    c.nsuper = S.nsuper;
+    if (const char* e = getenv("TLPB200_MERGE_LEVELS")) s->merge_levels = atoi(e) != 0;
     c.info = dalloc<int32_t>(s, 4);
     CK(cudaMemset(c.info, 0, 4 * sizeof(int32_t)));
     c.big_pack = upload(s, P.big_pack);
@@ -1473,6 +1510,31 @@ int tlpb200_debug_update_plan(const tlpb200_solver* s, int64_t* counts, int32_t*
             views[4 * i + 2] = P.oz_views[i].ncb;
             views[4 * i + 3] = P.oz_views[i].base_level;
         }
+    return TLPB200_OK;
+}
+
+// launch sequences of the triangular sweeps with merged levels (host data; tests/test_dense_solve_plan.py replays them):
+// counts[0..3] = #fwd ops, #bwd ops, #fwd items, #bwd items; ops as int32 records {kind, begin, end, level}; per-supernode
+// arrays of length nsuper; items as 24-byte SolveItem records {sn, blk, kind, r0, nr, pad}.  Any pointer may be NULL.
+int tlpb200_debug_solve_ops(const tlpb200_solver* s, int64_t* counts, int32_t* fwd_ops, int32_t* bwd_ops, int32_t* fwd_need,
+                            int32_t* fwd_parent, int32_t* bwd_wait, int32_t* bwd_nitems, void* fwd_items, void* bwd_seq, int32_t* sn_parent) {
+    if (!s) return TLPB200_BAD_ARG;
+    const Plan& P = s->plan;
+    static_assert(sizeof(SolveOp) == 16 && sizeof(SolveItem) == 24, "record sizes");
+    if (counts) {
+        counts[0] = (int64_t)P.fwd_ops.size(); counts[1] = (int64_t)P.bwd_ops.size();
+        counts[2] = (int64_t)P.fwd_items.size(); counts[3] = (int64_t)P.bwd_seq.size();
+    }
+    auto cp = [](void* dst, const void* src, size_t bytes) { if (dst && bytes) std::memcpy(dst, src, bytes); };
+    cp(fwd_ops, P.fwd_ops.data(), P.fwd_ops.size() * sizeof(SolveOp));
+    cp(bwd_ops, P.bwd_ops.data(), P.bwd_ops.size() * sizeof(SolveOp));
+    cp(fwd_need, P.fwd_need.data(), P.fwd_need.size() * 4);
+    cp(fwd_parent, P.fwd_parent.data(), P.fwd_parent.size() * 4);
+    cp(bwd_wait, P.bwd_wait.data(), P.bwd_wait.size() * 4);
+    cp(bwd_nitems, P.bwd_nitems.data(), P.bwd_nitems.size() * 4);
+    cp(fwd_items, P.fwd_items.data(), P.fwd_items.size() * sizeof(SolveItem));
+    cp(bwd_seq, P.bwd_seq.data(), P.bwd_seq.size() * sizeof(SolveItem));
+    cp(sn_parent, s->sym.sn_parent.data(), s->sym.sn_parent.size() * 4);
     return TLPB200_OK;
 }
 

@@ -97,6 +97,7 @@ struct tlpb200_solver {
     std::vector<cudaEvent_t> pool;
     std::vector<int> pool_cls;
     size_t pool_used = 0;
+    bool merge_levels = true;     // single GPU: block-solve items of consecutive levels share one launch (TLPB200_MERGE_LEVELS=0: per level)
     int scope_depth = 0;          // nesting depth of the profiling brackets (only the outermost records)
     double ms_class[TLPB200_NCLASS] = {0};
     int64_t n_class[TLPB200_NCLASS] = {0};
