@@ -172,11 +172,12 @@ int tlpb200_debug_big_plan(const tlpb200_solver* s, int64_t* counts, void* pack,
 /* Launch sequences of the triangular sweeps (host data, also on analyze_only handles): the block-solve items of consecutive
  * levels share one launch and synchronise through per-supernode counters.  counts[4] = #fwd ops, #bwd ops, #fwd items,
  * #bwd items; ops = int32 records {kind (0 small, 1 merged block-solve, 2 dense-solve, 3 below), begin, end, level};
- * fwd_need / fwd_parent / bwd_wait / bwd_nitems / sn_parent = per-supernode int32 arrays; items = 24-byte records
- * {sn, blk, kind, r0, nr, pad} in the order the sweeps walk them.  NULL pointers are skipped. */
+ * fwd_need / fwd_parent / bwd_wait / bwd_nitems / sn_parent / bwd_nbelow = per-supernode int32 arrays; items = 24-byte
+ * records {sn, blk, kind, r0, nr, pad} in the order the sweeps walk them (backward kind 2 = rows below the columns of a tall
+ * block-solve supernode, accumulated before its blocks).  NULL pointers are skipped. */
 int tlpb200_debug_solve_ops(const tlpb200_solver* s, int64_t* counts, int32_t* fwd_ops, int32_t* bwd_ops, int32_t* fwd_need,
                             int32_t* fwd_parent, int32_t* bwd_wait, int32_t* bwd_nitems, void* fwd_items, void* bwd_seq,
-                            int32_t* sn_parent);
+                            int32_t* sn_parent, int32_t* bwd_nbelow);
 
 /* ---- multi-GPU, one process per GPU (no counterpart in the reference, NEWS.md:31) -------------
  * Created with opt.nranks > 1 every rank analyses the same matrix, owns the elimination-tree subtrees

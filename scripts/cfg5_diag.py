@@ -22,3 +22,23 @@ for i in range(max(len(hl), len(dl))):
     b = dl[i] if i < len(dl) else None
     fmt = lambda r: "%2d pobj %.10e dobj %.10e pf %.2e df %.2e mu %.1e" % (r[0], r[1], r[2], r[3], r[4], r[6]) if r else "-"
     print("H", fmt(a), "| D", fmt(b))
+
+# state-leak checks: (a) device loop twice on the same fresh handle, (b) host IPM then device loop on the same handle
+k2 = pkg.setup(lp.A, pkg.K1(), pkg.Backend())
+d2 = pkg.DeviceHSD(k2, lp.b, lp.c, lp.l, lp.u, params=hsd.IPMOptions(IterationsLimit=40))
+for rep in range(3):
+    d2.optimize()
+    print("fresh handle, device run", rep, d2.status, d2.niter, "%.10e" % d2.primal_objective)
+k3 = pkg.setup(lp.A, pkg.K1(), pkg.Backend())
+h3 = hsd.HSD(lp.A, lp.b, lp.c, lp.l, lp.u, k3)
+h3.optimize(max_iter=40)
+print("same handle: host run", h3.status, h3.niter)
+d3 = pkg.DeviceHSD(k3, lp.b, lp.c, lp.l, lp.u, params=hsd.IPMOptions(IterationsLimit=40))
+for rep in range(2):
+    d3.optimize()
+    print("same handle after host run, device run", rep, d3.status, d3.niter, "%.10e" % d3.primal_objective)
+    for r in d3.log[14:22]:
+        print("   ", r)
+h4 = hsd.HSD(lp.A, lp.b, lp.c, lp.l, lp.u, k3)
+h4.optimize(max_iter=40)
+print("same handle: host run again", h4.status, h4.niter)

@@ -13,7 +13,8 @@ from tulip_jl_b200 import lpgen  # noqa: E402
 
 CASES = [("cfg3-mini", lambda: lpgen.staircase(stages=12, nodes=200, arcs=320, name="s"), "K2"),
          ("cfg4-mini", lambda: lpgen.block_angular(blocks=6, mb=400, nb=800, width=64, link=150, name="b"), "K1"),
-         ("cfg2-mini", lambda: lpgen.random_sparse(900, 1800, 6, name="r"), "K1")]
+         ("cfg2-mini", lambda: lpgen.random_sparse(900, 1800, 6, name="r"), "K1"),
+         ("tall-border", lambda: lpgen.block_angular(blocks=4, mb=600, nb=1200, width=96, link=500, name="b2"), "K1")]
 
 
 def _replay(items, begin, end, G, ready_fn, done_fn):
@@ -50,6 +51,7 @@ def test_merged_sweeps_replay(name, gen, sysname, G, ncol):
         if kind == 1:
             cover[b:e] += 1
     assert np.all(cover == 1)
+    assert np.array_equal(np.bincount(bit["sn"][bit["kind"] == 2], minlength=ns), ops["bwd_nbelow"])
     cover = np.zeros(len(bit), int)
     for kind, b, e, lvl in ops["bwd_ops"]:
         if kind == 1:
@@ -111,6 +113,7 @@ def test_merged_sweeps_replay(name, gen, sysname, G, ncol):
     bflag = {}
     bdone = np.zeros(ns, int)
     bdone_sn = np.zeros(ns, bool)
+    below_done = np.zeros(ns, int)
     big_bwd = k.big_plan()["bwd"]
     for kind, b, e, lvl in ops["bwd_ops"]:
         if kind == 3:
@@ -131,11 +134,19 @@ def test_merged_sweeps_replay(name, gen, sysname, G, ncol):
             w = ops["bwd_wait"][s]
             if w >= 0 and bdone[w] < ops["bwd_nitems"][w]:
                 return False
+            if it["kind"] == 2:
+                return True
+            if below_done[s] < ops["bwd_nbelow"][s]:
+                return False
             return all(bflag.get((s, j), False) for j in range(int(it["blk"]) + 1, ncb(s)))
 
         def done(x):
             it = bit[x]; s = int(it["sn"])
             p = par[s]
+            if it["kind"] == 2:            # rows below the columns: reads the ancestors' solution
+                assert p < 0 or bdone_sn[p] or (ops["bwd_nitems"][p] > 0 and bdone[p] == ops["bwd_nitems"][p]), ("below item early", s, p)
+                below_done[s] += 1
+                return
             if p >= 0:                     # the ancestors' solution is read here: the parent must be final
                 assert bdone_sn[p] or (ops["bwd_nitems"][p] > 0 and bdone[p] == ops["bwd_nitems"][p]), ("ancestor solution read early", s, p)
             bflag[(s, int(it["blk"]))] = True
@@ -144,7 +155,7 @@ def test_merged_sweeps_replay(name, gen, sysname, G, ncol):
         for x in range(b, e):
             if bdone[bit[x]["sn"]] == ops["bwd_nitems"][bit[x]["sn"]]:
                 bdone_sn[bit[x]["sn"]] = True
-    assert np.array_equal(bdone, ops["bwd_nitems"]) and bdone_sn.all()
+    assert np.array_equal(bdone, ops["bwd_nitems"]) and bdone_sn.all() and np.array_equal(below_done, ops["bwd_nbelow"])
     # a below op of level L sits after every op of a higher level in the sequence
     seen_lower = -1
     for kind, b, e, lvl in ops["bwd_ops"]:

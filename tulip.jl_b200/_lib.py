@@ -157,7 +157,7 @@ def load():
     lib.tlpb200_debug_chain_times.restype = C.c_int
     lib.tlpb200_debug_factor_trace.argtypes = [p, p, C.POINTER(C.c_int64)]
     lib.tlpb200_debug_factor_trace.restype = C.c_int
-    lib.tlpb200_debug_solve_ops.argtypes = [p, C.POINTER(C.c_int64), p, p, p, p, p, p, p, p, p]
+    lib.tlpb200_debug_solve_ops.argtypes = [p, C.POINTER(C.c_int64), p, p, p, p, p, p, p, p, p, p]
     lib.tlpb200_debug_solve_ops.restype = C.c_int
     lib.tlpb200_abi_sizes.argtypes = [C.POINTER(C.c_int32)]
     lib.tlpb200_abi_sizes.restype = None

@@ -412,6 +412,50 @@ __global__ void __launch_bounds__(SL_THREADS, 1) k_fwd_large(DevCtx c, int32_t b
     }
 }
 
+__device__ __forceinline__ void bwd_below_item(const DevCtx& c, int32_t s, int32_t i, int32_t br0, int32_t bnr, double* red) {
+    const int tid = threadIdx.x, r = tid & (SBLK - 1), cg = tid >> 7, lane = tid & 31, wq = (tid >> 5) & 3;
+    const int32_t f = c.sn_first[s];
+    const int32_t nc = c.sn_first[s + 1] - f;
+    const int64_t rp = c.sn_rowptr[s];
+    const int32_t ld = (int32_t)(c.sn_rowptr[s + 1] - rp);
+    const int32_t nbi = min(SBLK, nc - i * SBLK);
+    const double* colbase = c.Lx + c.sn_xptr[s] + (int64_t)(i * SBLK + cg * 32) * ld;
+    const int32_t ncv = min(32, max(0, nbi - cg * 32));
+    double p[32];
+#pragma unroll
+    for (int cc = 0; cc < 32; ++cc) p[cc] = 0.0;
+    const int32_t rend = br0 + bnr;
+#pragma unroll 1
+    for (int32_t r0 = br0; r0 < rend; r0 += SBLK) {
+        const int32_t rr = r0 + r;
+        if (rr < rend) {
+            const double xr = __ldcg(c.wk + c.sn_rows[rp + rr]);
+#pragma unroll
+            for (int c0 = 0; c0 < 32; c0 += 8) {   // 8 loads in flight per thread (keeps the kernel out of local memory)
+                double v[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] = (c0 + q < ncv) ? __ldcs(colbase + (int64_t)(c0 + q) * ld + rr) : 0.0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) p[c0 + q] += v[q] * xr;
+                asm volatile("" ::: "memory");
+            }
+        }
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int k = 0; k < off; ++k) {
+            const double send = up ? p[k] : p[k + off];
+            const double keep = up ? p[k + off] : p[k];
+            p[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    red[wq * SBLK + cg * 32 + lane] = p[0];
+    __syncthreads();
+    if (tid < nbi) atomicAdd(c.bacc + f + i * SBLK + tid, red[tid] + red[SBLK + tid] + red[2 * SBLK + tid] + red[3 * SBLK + tid]);
+}
+
 __global__ void __launch_bounds__(SL_THREADS, 1) k_bwd_large(DevCtx c, int32_t begin, int32_t end, int merged) {
     extern __shared__ double smem_d[];
     double* Ds = smem_d;                   // [SBLK*SBLK] transposed inverse of the item's diagonal block
@@ -425,6 +469,16 @@ __global__ void __launch_bounds__(SL_THREADS, 1) k_bwd_large(DevCtx c, int32_t b
         if (c.skip && c.skip[s]) continue;
         // merged levels: x of every ancestor is final once all items of the in-launch parent have finished
         if (merged && c.bwd_wait[s] >= 0) wait_count(c.dep_cnt + c.nsuper + c.bwd_wait[s], c.bwd_nitems[c.bwd_wait[s]], c.info);
+        if (merged && I.kind == 2) {
+            // rows below the columns of a tall supernode (what k_bwd_below does in the per-level path): accumulate into bacc,
+            // then tell the supernode's block items that one more below item is in place
+            bwd_below_item(c, s, I.blk, I.r0, I.nr, red);
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) atomicAdd(c.dep_cnt + 2 * c.nsuper + s, 1);
+            continue;
+        }
+        if (merged && c.bwd_nbelow[s] > 0) wait_count(c.dep_cnt + 2 * c.nsuper + s, c.bwd_nbelow[s], c.info);
         const int32_t f = c.sn_first[s];
         const int32_t nc = c.sn_first[s + 1] - f;
         const int64_t rp = c.sn_rowptr[s];
@@ -541,50 +595,8 @@ __global__ void __launch_bounds__(SL_THREADS, 1) k_bwd_large(DevCtx c, int32_t b
 __global__ void __launch_bounds__(SL_THREADS, 1) k_bwd_below(DevCtx c, int32_t begin) {
     __shared__ double red[SL_CG * SBLK];
     const BelowItem I = c.bwd_below[begin + blockIdx.x];
-    const int32_t s = I.sn;
-    if (c.skip && c.skip[s]) return;
-    const int tid = threadIdx.x, r = tid & (SBLK - 1), cg = tid >> 7, lane = tid & 31, wq = (tid >> 5) & 3;
-    const int32_t f = c.sn_first[s];
-    const int32_t nc = c.sn_first[s + 1] - f;
-    const int64_t rp = c.sn_rowptr[s];
-    const int32_t ld = (int32_t)(c.sn_rowptr[s + 1] - rp);
-    const int32_t i = I.blk;
-    const int32_t nbi = min(SBLK, nc - i * SBLK);
-    const double* colbase = c.Lx + c.sn_xptr[s] + (int64_t)(i * SBLK + cg * 32) * ld;
-    const int32_t ncv = min(32, max(0, nbi - cg * 32));
-    double p[32];
-#pragma unroll
-    for (int cc = 0; cc < 32; ++cc) p[cc] = 0.0;
-    const int32_t rend = I.r0 + I.nr;
-#pragma unroll 1
-    for (int32_t r0 = I.r0; r0 < rend; r0 += SBLK) {
-        const int32_t rr = r0 + r;
-        if (rr < rend) {
-            const double xr = __ldcg(c.wk + c.sn_rows[rp + rr]);
-#pragma unroll
-            for (int c0 = 0; c0 < 32; c0 += 8) {   // 8 loads in flight per thread (keeps the kernel out of local memory)
-                double v[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) v[q] = (c0 + q < ncv) ? __ldcs(colbase + (int64_t)(c0 + q) * ld + rr) : 0.0;
-#pragma unroll
-                for (int q = 0; q < 8; ++q) p[c0 + q] += v[q] * xr;
-                asm volatile("" ::: "memory");
-            }
-        }
-    }
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-        const bool up = (lane & off) != 0;
-#pragma unroll
-        for (int k = 0; k < off; ++k) {
-            const double send = up ? p[k] : p[k + off];
-            const double keep = up ? p[k + off] : p[k];
-            p[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-        }
-    }
-    red[wq * SBLK + cg * 32 + lane] = p[0];
-    __syncthreads();
-    if (tid < nbi) atomicAdd(c.bacc + f + i * SBLK + tid, red[tid] + red[SBLK + tid] + red[2 * SBLK + tid] + red[3 * SBLK + tid]);
+    if (c.skip && c.skip[I.sn]) return;
+    bwd_below_item(c, I.sn, I.blk, I.r0, I.nr, red);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -62,7 +62,9 @@ struct DevCtx {
     const int32_t* sn_split;       // [nsuper] 1 = rows below the columns are accumulated into bacc by k_bwd_below
     double* bacc;                  // [N] backward accumulator sum_rows L[row, c] x[row]; consumers re-zero their entries
     // merged-level sweeps (Plan::SolveOp): per-supernode dependency counters and their static targets
-    int32_t* dep_cnt;              // [2 * nsuper] forward: finished items of in-launch children / backward: finished items; zeroed per solve
+    int32_t* dep_cnt;              // [3 * nsuper] forward: finished items of in-launch children / backward: finished items /
+                                   // backward: finished below items; zeroed per solve
+    const int32_t* bwd_nbelow;     // [nsuper]
     const int32_t* fwd_need;       // [nsuper]
     const int32_t* fwd_parent;     // [nsuper]
     const int32_t* bwd_wait;       // [nsuper]

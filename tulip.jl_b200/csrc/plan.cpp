@@ -532,11 +532,27 @@ void build_plan(const Symbolic& S, const PlanOptions& opt, Plan& P) {
                 P.fwd_need[par] += fitems[s2];
             }
         }
-        // backward: levels descending; per level the launch order is below, big, large, small
-        std::vector<int32_t> seq_b(nlev, 0), seq_e(nlev, 0);
+        // backward: levels descending; per level the launch order is below, big, large, small.  The below items of the
+        // dense-solve supernodes stay a launch of their own (the dense-solve launch that follows breaks the run anyway);
+        // those of the block-solve supernodes join the merged sequence as items of kind 2, ahead of their level's blocks.
+        P.bwd_nbelow.assign(S.nsuper, 0);
+        std::vector<int32_t> seq_b(nlev, 0), seq_e(nlev, 0), below_big_end(nlev, 0);
         for (int32_t L = nlev - 1; L >= 0; --L) {
             const LevelPlan& lp = P.levels[L];
             seq_b[L] = (int32_t)P.bwd_seq.size();
+            below_big_end[L] = lp.below_begin;
+            for (int32_t x = lp.below_begin; x < lp.below_end; ++x) {
+                const BelowItem& bi = P.bwd_below[x];
+                if (P.sn_big[bi.sn]) {
+                    if (x != below_big_end[L]) throw std::logic_error("below items: dense-solve supernodes are expected first");
+                    below_big_end[L] = x + 1;
+                    continue;
+                }
+                SolveItem it;
+                it.sn = bi.sn; it.blk = bi.blk; it.kind = 2; it.r0 = bi.r0; it.nr = bi.nr; it.pad = 0;
+                P.bwd_seq.push_back(it);
+                P.bwd_nbelow[bi.sn]++;
+            }
             for (int32_t x = lp.bwd_begin; x < lp.bwd_end; ++x) { P.bwd_seq.push_back(P.bwd_items[x]); P.bwd_nitems[P.bwd_items[x].sn]++; }
             seq_e[L] = (int32_t)P.bwd_seq.size();
         }
@@ -547,7 +563,7 @@ void build_plan(const Symbolic& S, const PlanOptions& opt, Plan& P) {
         };
         for (int32_t L = nlev - 1; L >= 0; --L) {
             const LevelPlan& lp = P.levels[L];
-            if (lp.below_end > lp.below_begin) { flush_b(); P.bwd_ops.push_back(SolveOp{3, lp.below_begin, lp.below_end, L}); }
+            if (below_big_end[L] > lp.below_begin) { flush_b(); P.bwd_ops.push_back(SolveOp{3, lp.below_begin, below_big_end[L], L}); }
             if (lp.bbig_end > lp.bbig_begin) { flush_b(); P.bwd_ops.push_back(SolveOp{2, lp.bbig_begin, lp.bbig_end, L}); }
             if (seq_e[L] > seq_b[L]) {
                 if (pend_b >= 0 && pend_e != seq_b[L]) flush_b();

@@ -157,6 +157,7 @@ struct Plan {
     std::vector<int32_t> fwd_parent;         // [nsuper] forward: in-launch parent to notify (-1: none)
     std::vector<int32_t> bwd_wait;           // [nsuper] backward: in-launch parent to wait for (-1: none)
     std::vector<int32_t> bwd_nitems;         // [nsuper] backward items of the supernode (= its column blocks)
+    std::vector<int32_t> bwd_nbelow;         // [nsuper] below items (kind 2) of a block-solve supernode inside the merged sequence
     std::vector<Piece> pieces;
     std::vector<int32_t> sn_small;        // [nsuper] 1 = handled by the one-CTA kernels
     std::vector<int32_t> sn_level;        // [nsuper] level of the supernode's last item

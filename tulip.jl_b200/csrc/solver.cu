@@ -417,7 +417,7 @@ void enqueue_factor(tlpb200_solver* s, int64_t& count) {
 // hand-over state of one forward + backward sweep: "block solved" flags and the dependency counters of the merged levels
 // (allocated back to back: flags [2 * ndblk], then dep_cnt [2 * nsuper])
 void reset_sweep_state(tlpb200_solver* s, cudaStream_t st) {
-    const size_t n = (size_t)2 * s->ctx.ndblk + (size_t)2 * s->sym.nsuper;
+    const size_t n = (size_t)2 * s->ctx.ndblk + (size_t)3 * s->sym.nsuper;
     if (n > 0) CK(cudaMemsetAsync(s->ctx.flags, 0, n * sizeof(int32_t), st));
 }
 
@@ -814,13 +814,14 @@ void setup_device(tlpb200_solver* s) {
     c.Dinv = dalloc<double>(s, (size_t)P.ndblk * SBLK * SBLK);
     c.DinvT = dalloc<double>(s, (size_t)P.ndblk * SBLK * SBLK);
     c.LsubT = dalloc<double>(s, (size_t)P.ndblk * SBLK * SBLK);
-    c.flags = dalloc<int32_t>(s, (size_t)2 * P.ndblk + (size_t)2 * S.nsuper);
-    CK(cudaMemset(c.flags, 0, std::max<size_t>((size_t)2 * P.ndblk + (size_t)2 * S.nsuper, 1) * sizeof(int32_t)));
+    c.flags = dalloc<int32_t>(s, (size_t)2 * P.ndblk + (size_t)3 * S.nsuper);
+    CK(cudaMemset(c.flags, 0, std::max<size_t>((size_t)2 * P.ndblk + (size_t)3 * S.nsuper, 1) * sizeof(int32_t)));
     c.dep_cnt = c.flags + (size_t)2 * P.ndblk;
     c.fwd_need = upload(s, P.fwd_need);
     c.fwd_parent = upload(s, P.fwd_parent);
     c.bwd_wait = upload(s, P.bwd_wait);
     c.bwd_nitems = upload(s, P.bwd_nitems);
+    c.bwd_nbelow = upload(s, P.bwd_nbelow);
     c.bwd_seq = upload(s, P.bwd_seq);
     c.nsuper = S.nsuper;
     if (const char* e = getenv("TLPB200_MERGE_LEVELS")) s->merge_levels = atoi(e) != 0;
@@ -1517,7 +1518,8 @@ int tlpb200_debug_update_plan(const tlpb200_solver* s, int64_t* counts, int32_t*
 // counts[0..3] = #fwd ops, #bwd ops, #fwd items, #bwd items; ops as int32 records {kind, begin, end, level}; per-supernode
 // arrays of length nsuper; items as 24-byte SolveItem records {sn, blk, kind, r0, nr, pad}.  Any pointer may be NULL.
 int tlpb200_debug_solve_ops(const tlpb200_solver* s, int64_t* counts, int32_t* fwd_ops, int32_t* bwd_ops, int32_t* fwd_need,
-                            int32_t* fwd_parent, int32_t* bwd_wait, int32_t* bwd_nitems, void* fwd_items, void* bwd_seq, int32_t* sn_parent) {
+                            int32_t* fwd_parent, int32_t* bwd_wait, int32_t* bwd_nitems, void* fwd_items, void* bwd_seq, int32_t* sn_parent,
+                            int32_t* bwd_nbelow) {
     if (!s) return TLPB200_BAD_ARG;
     const Plan& P = s->plan;
     static_assert(sizeof(SolveOp) == 16 && sizeof(SolveItem) == 24, "record sizes");
@@ -1535,6 +1537,7 @@ int tlpb200_debug_solve_ops(const tlpb200_solver* s, int64_t* counts, int32_t* f
     cp(fwd_items, P.fwd_items.data(), P.fwd_items.size() * sizeof(SolveItem));
     cp(bwd_seq, P.bwd_seq.data(), P.bwd_seq.size() * sizeof(SolveItem));
     cp(sn_parent, s->sym.sn_parent.data(), s->sym.sn_parent.size() * 4);
+    cp(bwd_nbelow, P.bwd_nbelow.data(), P.bwd_nbelow.size() * 4);
     return TLPB200_OK;
 }
 

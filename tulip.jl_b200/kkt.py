@@ -348,17 +348,18 @@ class B200KKTSolver:
         """Launch sequences of the triangular sweeps with merged levels (host data, available on analyze_only handles)."""
         lib = _lib.load()
         cnt = np.zeros(4, np.int64)
-        none9 = [None] * 9
-        lib.tlpb200_debug_solve_ops(self._h, cnt.ctypes.data_as(C.POINTER(C.c_int64)), *none9)
+        none10 = [None] * 10
+        lib.tlpb200_debug_solve_ops(self._h, cnt.ctypes.data_as(C.POINTER(C.c_int64)), *none10)
         ns = self.stats()["nsuper"]
+        nbel = np.zeros(ns, np.int32)
         fo = np.zeros((int(cnt[0]), 4), np.int32); bo = np.zeros((int(cnt[1]), 4), np.int32)
         need = np.zeros(ns, np.int32); fpar = np.zeros(ns, np.int32); bwait = np.zeros(ns, np.int32); bn = np.zeros(ns, np.int32)
         fit = np.zeros(int(cnt[2]), self.ITEM_DTYPE); bit = np.zeros(int(cnt[3]), self.ITEM_DTYPE); par = np.zeros(ns, np.int32)
         vp = lambda a: C.c_void_p(a.ctypes.data)
         lib.tlpb200_debug_solve_ops(self._h, cnt.ctypes.data_as(C.POINTER(C.c_int64)), vp(fo), vp(bo), vp(need), vp(fpar), vp(bwait),
-                                    vp(bn), vp(fit), vp(bit), vp(par))
+                                    vp(bn), vp(fit), vp(bit), vp(par), vp(nbel))
         return dict(fwd_ops=fo, bwd_ops=bo, fwd_need=need, fwd_parent=fpar, bwd_wait=bwait, bwd_nitems=bn, fwd_items=fit,
-                    bwd_seq=bit, sn_parent=par)
+                    bwd_seq=bit, sn_parent=par, bwd_nbelow=nbel)
 
     def big_plan(self):
         """Dense-solve plan of the big supernodes (host data, available on analyze_only handles)."""
