@@ -232,6 +232,7 @@ int tlpb200_hsd_create(tlpb200_solver* s, const double* b, const double* c, cons
         d.rp = dvec(s, m); d.rl = dvec(s, n); d.ru = dvec(s, n); d.rd = dvec(s, n);
         d.ixl = dvec(s, n); d.ixu = dvec(s, n); d.thl = dvec(s, n); d.thu = dvec(s, n); d.cbar = dvec(s, n);
         d.hx = dvec(s, n); d.hy = dvec(s, m); d.wl = dvec(s, n); d.wu = dvec(s, n);
+        d.aty_long = dvec(s, (size_t)std::max<int32_t>(s->mat.nlong, 1));
         d.sc = dvec(s, SC_COUNT);
         d.part = dvec(s, (size_t)IPM_MAXBLOCKS * IPM_NRED);
         CKI(cudaMemset(d.sc, 0, SC_COUNT * sizeof(double)));

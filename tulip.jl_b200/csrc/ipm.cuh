@@ -51,6 +51,7 @@ struct IpmDev {
     double *rp, *rl, *ru, *rd;
     // work vectors of compute_step! (step.jl:24-26, :55-60)
     double *ixl, *ixu, *thl, *thu, *cbar, *hx, *hy, *wl, *wu;
+    double* aty_long;   // [nlong] A'y of the long columns (k_ipm_aty_long)
     double* sc;      // [SC_COUNT] device scalars
     double* part;    // [IPM_MAXBLOCKS][IPM_NRED] per-block partials of the fused reductions
 };

@@ -614,37 +614,37 @@ __global__ void k_k1_rhs(DevCtx c, DevMat A, const double* __restrict__ d, const
     c.wk[c.iperm[i]] = v;
 }
 
-// v_j = sum_p A[p, j] y[iperm[row_p]] with one thread per column; a column longer than 64 entries (the dense columns of
-// BASELINE config 5 hold 25 000) is walked by its whole warp instead of one lane (measured: 4.8 ms -> the serial lane was the
-// whole cost of rhs + recovery on config 5).  Every lane of the warp must call this.
-__device__ __forceinline__ double col_dot_perm(const DevMat& A, const int32_t* __restrict__ iperm, const double* __restrict__ y,
-                                               int64_t j, int64_t row_shift) {
-    const int lane = threadIdx.x & 31;
-    const int64_t b = (j < A.n) ? A.colptr[j] : 0, e = (j < A.n) ? A.colptr[j + 1] : 0;
-    const bool is_long = e - b > 64;
-    double v = 0.0;
-    if (!is_long)
-        for (int64_t p = b; p < e; ++p) v += A.val[p] * y[iperm[row_shift + A.rowidx[p]]];
-    unsigned mask = __ballot_sync(0xffffffffu, is_long);
-    while (mask) {
-        const int src = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const int64_t bb = __shfl_sync(0xffffffffu, b, src), ee = __shfl_sync(0xffffffffu, e, src);
-        double a = 0.0;
-        for (int64_t p = bb + lane; p < ee; p += 32) a += A.val[p] * y[iperm[row_shift + A.rowidx[p]]];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        if (lane == src) v = a;
-    }
-    return v;
-}
-
+// dx_j = d_j (sum_p A[p, j] dy[row_p] - xi_d_j) with one thread per column; a column longer than LONG_COL entries (the dense
+// columns of BASELINE config 5 hold 25 000) is left to k_k1_recover_long, one CTA per column (a single lane walking it was the
+// whole cost of rhs + recovery on config 5: 4.8 ms; a warp per column still serialised the eight adjacent dense columns: 3.1 ms)
 __global__ void k_k1_recover(DevCtx c, DevMat A, const double* __restrict__ d, const double* __restrict__ xi_d,
                              double* __restrict__ dx, double* __restrict__ dy) {
     const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const double v = col_dot_perm(A, c.iperm, c.wk, j, 0);
-    if (j < A.n) dx[j] = d[j] * (v - xi_d[j]);
+    if (j < A.n) {
+        const int64_t b = A.colptr[j], e = A.colptr[j + 1];
+        if (e - b <= LONG_COL) {
+            double v = 0.0;
+            for (int64_t p = b; p < e; ++p) v += A.val[p] * c.wk[c.iperm[A.rowidx[p]]];
+            dx[j] = d[j] * (v - xi_d[j]);
+        }
+    }
     if (j < A.m) dy[j] = c.wk[c.iperm[j]];
+}
+__global__ void __launch_bounds__(256) k_k1_recover_long(DevCtx c, DevMat A, const double* __restrict__ d, const double* __restrict__ xi_d,
+                                                        double* __restrict__ dx) {
+    __shared__ double red[8];
+    const int64_t j = A.long_cols[blockIdx.x];
+    double v = 0.0;
+    for (int64_t p = A.colptr[j] + threadIdx.x; p < A.colptr[j + 1]; p += blockDim.x) v += A.val[p] * c.wk[c.iperm[A.rowidx[p]]];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        dx[j] = d[j] * (t - xi_d[j]);
+    }
 }
 
 __global__ void k_k2_rhs(DevCtx c, DevMat A, const double* __restrict__ xi_p, const double* __restrict__ xi_d) {
@@ -766,6 +766,7 @@ void launch_k1_recover(const DevCtx& c, const DevMat& A, const double* d, const 
                        cudaStream_t st) {
     const int64_t mx = A.n > A.m ? A.n : A.m;
     if (mx > 0) k_k1_recover<<<nblk(mx, 128), 128, 0, st>>>(c, A, d, xi_d, dx, dy);
+    if (A.nlong > 0) k_k1_recover_long<<<A.nlong, 256, 0, st>>>(c, A, d, xi_d, dx);
 }
 void launch_k2_rhs(const DevCtx& c, const DevMat& A, const double* xi_p, const double* xi_d, cudaStream_t st) {
     if (A.n + A.m > 0) k_k2_rhs<<<nblk(A.n + A.m, 256), 256, 0, st>>>(c, A, xi_p, xi_d);

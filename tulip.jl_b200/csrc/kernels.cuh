@@ -102,7 +102,12 @@ struct DevMat {
     const double* w_val;
     // K2 assemble
     const int64_t* a_dest;
+    // columns with more than LONG_COL non-zeros (the dense columns of BASELINE config 5): the per-column kernels leave them
+    // to one CTA each instead of one thread
+    const int32_t* long_cols;   // [nlong] sorted
+    int32_t nlong;
 };
+constexpr int LONG_COL = 64;
 
 // dense columns of A handled outside the sparse factorisation (K1 only, see kernels_dense_cols.cu)
 struct DenseCols {

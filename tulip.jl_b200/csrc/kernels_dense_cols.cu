@@ -145,25 +145,21 @@ __global__ void k_dc_apply(DevCtx c, DenseCols dc) {
 // ill-conditioned, which it is near IPM convergence):  r = xi - (A D A' + Rd) y, all in permuted row order
 __global__ void k_dc_at_y(DevCtx c, DevMat A, const double* __restrict__ d, const double* __restrict__ y, double* __restrict__ tn) {
     const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    // one thread per column, a whole warp for a long (dense) column
-    const int lane = threadIdx.x & 31;
-    const int64_t b = (j < A.n) ? A.colptr[j] : 0, e = (j < A.n) ? A.colptr[j + 1] : 0;
-    const bool is_long = e - b > 64;
+    if (j >= A.n) return;
+    const int64_t b = A.colptr[j], e = A.colptr[j + 1];
+    if (e - b > LONG_COL) return;            // one CTA per long column: k_dc_at_y_long
     double v = 0.0;
-    if (!is_long)
-        for (int64_t p = b; p < e; ++p) v += A.val[p] * y[c.iperm[A.rowidx[p]]];
-    unsigned mask = __ballot_sync(0xffffffffu, is_long);
-    while (mask) {
-        const int src = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const int64_t bb = __shfl_sync(0xffffffffu, b, src), ee = __shfl_sync(0xffffffffu, e, src);
-        double a = 0.0;
-        for (int64_t p = bb + lane; p < ee; p += 32) a += A.val[p] * y[c.iperm[A.rowidx[p]]];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        if (lane == src) v = a;
-    }
-    if (j < A.n) tn[j] = d[j] * v;
+    for (int64_t p = b; p < e; ++p) v += A.val[p] * y[c.iperm[A.rowidx[p]]];
+    tn[j] = d[j] * v;
+}
+__global__ void __launch_bounds__(256) k_dc_at_y_long(DevCtx c, DevMat A, const double* __restrict__ d, const double* __restrict__ y,
+                                                     double* __restrict__ tn) {
+    __shared__ double red[32];
+    const int64_t j = A.long_cols[blockIdx.x];
+    double v = 0.0;
+    for (int64_t p = A.colptr[j] + threadIdx.x; p < A.colptr[j + 1]; p += blockDim.x) v += A.val[p] * y[c.iperm[A.rowidx[p]]];
+    v = block_sum(v, red);
+    if (threadIdx.x == 0) tn[j] = d[j] * v;
 }
 __global__ void k_dc_residual(DevCtx c, DevMat A, const double* __restrict__ regD, const double* __restrict__ xi,
                               const double* __restrict__ y, const double* __restrict__ tn) {
@@ -204,6 +200,7 @@ void launch_k2_residual(const DevCtx& c, const DevMat& A, const double* theta, c
 void launch_dc_residual(const DevCtx& c, const DevMat& A, const double* d, const double* regD, const double* xi, const double* y,
                         double* tn, cudaStream_t st) {
     k_dc_at_y<<<(unsigned)((A.n + 127) / 128), 128, 0, st>>>(c, A, d, y, tn);
+    if (A.nlong > 0) k_dc_at_y_long<<<A.nlong, 256, 0, st>>>(c, A, d, y, tn);
     k_dc_residual<<<(unsigned)((A.m + 127) / 128), 128, 0, st>>>(c, A, regD, xi, y, tn);
 }
 void launch_dc_axpy(const DevCtx& c, const double* y, cudaStream_t st) {

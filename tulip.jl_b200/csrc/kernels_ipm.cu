@@ -69,7 +69,14 @@ __global__ void __launch_bounds__(IPM_THREADS) k_ipm_residuals(IpmDev d, DevMat 
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < mx; i += (int64_t)gridDim.x * blockDim.x) {
         if (i < A.n) {
             double aty = 0.0;
-            for (int64_t p = A.colptr[i]; p < A.colptr[i + 1]; ++p) aty += A.val[p] * d.y[A.rowidx[p]];
+            const int64_t cb = A.colptr[i], ce = A.colptr[i + 1];
+            if (ce - cb <= LONG_COL) {
+                for (int64_t p = cb; p < ce; ++p) aty += A.val[p] * d.y[A.rowidx[p]];
+            } else {          // long column: A'y was formed by k_ipm_aty_long (one CTA per column); find its slot
+                int lo = 0, hi = A.nlong - 1;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (A.long_cols[mid] < (int32_t)i) lo = mid + 1; else hi = mid; }
+                aty = d.aty_long[lo];
+            }
             const double lf = d.lf[i], uf = d.uf[i], x = d.x[i], xl = d.xl[i], xu = d.xu[i], zl = d.zl[i], zu = d.zu[i];
             const double lm = d.lm[i], um = d.um[i], c = d.c[i];
             const double rl = lf != 0.0 ? (-x + xl + tau * lm) : 0.0;
@@ -92,6 +99,23 @@ __global__ void __launch_bounds__(IPM_THREADS) k_ipm_residuals(IpmDev d, DevMat 
         }
     }
     block_partials<13>(v, ops, d.part);
+}
+
+// A'y of the long columns, one CTA per column (feeds k_ipm_residuals)
+__global__ void __launch_bounds__(256) k_ipm_aty_long(IpmDev d, DevMat A) {
+    __shared__ double red[8];
+    const int64_t j = A.long_cols[blockIdx.x];
+    double v = 0.0;
+    for (int64_t p = A.colptr[j] + threadIdx.x; p < A.colptr[j + 1]; p += blockDim.x) v += A.val[p] * d.y[A.rowidx[p]];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        d.aty_long[blockIdx.x] = t;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -387,6 +411,7 @@ void ipm_launch_start(const IpmDev& d, int64_t n, int64_t m, double* regP, doubl
 
 void ipm_launch_residuals(const IpmDev& d, const DevMat& A, const IpmScalars& P, cudaStream_t st) {
     const int g = ipm_grid(A.n > A.m ? A.n : A.m);
+    if (A.nlong > 0) k_ipm_aty_long<<<A.nlong, 256, 0, st>>>(d, A);
     k_ipm_residuals<<<g, IPM_THREADS, 0, st>>>(d, A);
     const int ops[13] = {RMAX, RMAX, RMAX, RSUM, RSUM, RSUM, RSUM, RMAX, RMAX, RMAX, RMAX, RSUM, RMAX};
     finish(d, PH_RESIDUALS, g, 13, ops, 0, 0, P, st);

@@ -931,6 +931,13 @@ void setup_device(tlpb200_solver* s) {
         A.colidx = upload(s, ci);
         A.rval = upload(s, rv);
     }
+    {
+        std::vector<int32_t> lc;
+        for (int64_t j = 0; j < s->n; ++j)
+            if (s->colptr[j + 1] - s->colptr[j] > LONG_COL) lc.push_back((int32_t)j);
+        A.nlong = (int32_t)lc.size();
+        A.long_cols = upload(s, lc);
+    }
     A.nentries = (int64_t)s->maps.w_dest.size();
     A.w_ptr = upload(s, s->maps.w_ptr);
     A.w_dest = upload(s, s->maps.w_dest);
