@@ -514,3 +514,33 @@ def test_dense_columns_full_size_ipm_converges():
     assert h.niter <= 20
     assert abs(h.primal_objective - 50833.48157246) <= 1e-7 * 50833.48157246
     assert abs(h.primal_objective - h.dual_objective) <= 1e-8 * (1 + abs(h.dual_objective))
+
+
+@pytest.mark.parametrize("cfg,sysname", [(3, "K2"), (4, "K1"), (2, "K1")])
+def test_merged_level_sweeps_match_per_level_sweeps(cfg, sysname, monkeypatch):
+    """Round 2: the block-solve items of consecutive levels share one persistent launch and synchronise through per-supernode
+    counters (Plan::SolveOp).  At BASELINE size (config 3: a chain of ~95 levels) the merged sweeps must give the solutions
+    of the per-level launches (TLPB200_MERGE_LEVELS=0) up to the rounding of the atomic accumulations, for many right-hand
+    sides in a row on the same factor (the counters are reset per solve), and use fewer launches."""
+    lp = lpgen.config(cfg)
+    A = lp.A
+    m, n = A.shape
+    rng = np.random.default_rng(41)
+    theta = np.exp(rng.uniform(-3, 3, n)); regP = np.full(n, 1e-5); regD = np.full(m, 1e-5)
+    monkeypatch.setenv("TLPB200_MERGE_LEVELS", "0")
+    k0 = pkg.setup(A, SYSTEMS[sysname](), pkg.Backend())
+    monkeypatch.setenv("TLPB200_MERGE_LEVELS", "1")
+    k1 = pkg.setup(A, SYSTEMS[sysname](), pkg.Backend())
+    k0.update(theta, regP, regD); k1.update(theta, regP, regD)
+    worst = 0.0
+    for rep in range(12):
+        xi_p = rng.standard_normal(m); xi_d = rng.standard_normal(n)
+        a = [np.zeros(n), np.zeros(m)]; b = [np.zeros(n), np.zeros(m)]
+        k0.solve(a[0], a[1], xi_p, xi_d)
+        k1.solve(b[0], b[1], xi_p, xi_d)
+        ref = max(np.abs(a[0]).max(), np.abs(a[1]).max())
+        worst = max(worst, np.abs(a[0] - b[0]).max() / ref, np.abs(a[1] - b[1]).max() / ref)
+        rp, rd = kkt_ref.kkt_residuals(A, theta, regP, regD, b[0], b[1], xi_p, xi_d)
+        assert rp <= SQRT_EPS * max(1.0, ref) and rd <= SQRT_EPS * max(1.0, ref)
+    assert worst <= 1e-9, worst
+    assert k1.stats()["launches_solve"] < k0.stats()["launches_solve"]
