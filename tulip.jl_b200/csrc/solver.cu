@@ -190,6 +190,7 @@ void build_work_prefix(tlpb200_solver* s) {
         fill(tlpb200_solver::WL_BELOW, P.bwd_below.size(), [&](size_t i) { return P.bwd_below[i].sn; });
         fill(tlpb200_solver::WL_INV, P.inv_order.size(), [&](size_t i) { return P.dblk_sn[P.inv_order[i]]; });
         fill(tlpb200_solver::WL_PACK, P.big_pack.size(), [&](size_t i) { return P.big_pack[i].sn; });
+        fill(tlpb200_solver::WL_BSEQ, P.bwd_seq.size(), [&](size_t i) { return P.bwd_seq[i].sn; });
     }
 }
 
@@ -434,12 +435,15 @@ void enqueue_rhs(tlpb200_solver* s, const double* xip, const double* xid, int64_
 
 void enqueue_fwd(tlpb200_solver* s, int64_t& count) {
     cudaStream_t st = s->stream;
-    if (s->cur == &s->ctx && s->merge_levels) {
-        // single GPU: the plan's launch sequence with the block-solve items of consecutive levels merged (Plan::SolveOp)
+    if (s->merge_levels) {
+        // the plan's launch sequence with the block-solve items of consecutive levels merged (Plan::SolveOp); a sharded phase
+        // walks the same sequence with its own dependency targets (ctxA / ctxB) and drops the ops it has no item in
         for (const SolveOp& op : s->plan.fwd_ops) {
-            if (op.kind == 0) { Scope sc(s, 6); launch_fwd_small(s->ctx, op.begin, op.end, st); }
-            else if (op.kind == 1) { Scope sc(s, 7); launch_fwd_large(s->ctx, op.begin, op.end, s->nsm, 1, st); }
-            else { Scope sc(s, 14); launch_fwd_big(s->ctx, op.begin, op.end, s->nsm, st); }
+            const int wl = op.kind == 0 ? tlpb200_solver::WL_SMALL : (op.kind == 1 ? tlpb200_solver::WL_FWD : tlpb200_solver::WL_FBIG);
+            if (!has_work(s, wl, op.begin, op.end)) continue;
+            if (op.kind == 0) { Scope sc(s, 6); launch_fwd_small((*s->cur), op.begin, op.end, st); }
+            else if (op.kind == 1) { Scope sc(s, 7); launch_fwd_large((*s->cur), op.begin, op.end, s->nsm, 1, st); }
+            else { Scope sc(s, 14); launch_fwd_big((*s->cur), op.begin, op.end, s->nsm, st); }
             count++;
         }
         return;
@@ -455,12 +459,15 @@ void enqueue_fwd(tlpb200_solver* s, int64_t& count) {
 
 void enqueue_bwd(tlpb200_solver* s, int64_t& count) {
     cudaStream_t st = s->stream;
-    if (s->cur == &s->ctx && s->merge_levels) {
+    if (s->merge_levels) {
         for (const SolveOp& op : s->plan.bwd_ops) {
-            if (op.kind == 3) { Scope sc(s, 9); launch_bwd_below(s->ctx, op.begin, op.end, st); }
-            else if (op.kind == 2) { Scope sc(s, 15); launch_bwd_big(s->ctx, op.begin, op.end, s->nsm, st); }
-            else if (op.kind == 1) { Scope sc(s, 9); launch_bwd_large(s->ctx, op.begin, op.end, s->nsm, 1, st); }
-            else { Scope sc(s, 11); launch_bwd_small(s->ctx, op.begin, op.end, st); }
+            const int wl = op.kind == 3 ? tlpb200_solver::WL_BELOW : (op.kind == 2 ? tlpb200_solver::WL_BBIG
+                         : (op.kind == 1 ? tlpb200_solver::WL_BSEQ : tlpb200_solver::WL_SMALL));
+            if (!has_work(s, wl, op.begin, op.end)) continue;
+            if (op.kind == 3) { Scope sc(s, 9); launch_bwd_below((*s->cur), op.begin, op.end, st); }
+            else if (op.kind == 2) { Scope sc(s, 15); launch_bwd_big((*s->cur), op.begin, op.end, s->nsm, st); }
+            else if (op.kind == 1) { Scope sc(s, 9); launch_bwd_large((*s->cur), op.begin, op.end, s->nsm, 1, st); }
+            else { Scope sc(s, 11); launch_bwd_small((*s->cur), op.begin, op.end, st); }
             count++;
         }
         return;
@@ -865,6 +872,28 @@ void setup_device(tlpb200_solver* s) {
         }
         s->ctxA = s->ctx; s->ctxA.skip = upload(s, skipA);
         s->ctxB = s->ctx; s->ctxB.skip = upload(s, skipB);
+        // merged-level sweeps inside a phase: a supernode only waits for / notifies supernodes that run in the SAME phase (a
+        // subtree root's parent belongs to the top part: in the forward sweep it runs in a later phase, in the backward sweep
+        // it is complete before the phase starts)
+        {
+            std::vector<int32_t> fitems(S.nsuper, 0);
+            for (const SolveItem& it : P.fwd_items) fitems[it.sn]++;
+            for (int ph = 0; ph < 2; ++ph) {
+                const std::vector<int8_t>& skip = ph == 0 ? skipA : skipB;
+                std::vector<int32_t> need(S.nsuper, 0), fpar(S.nsuper, -1), bwait(S.nsuper, -1);
+                for (int32_t sn = 0; sn < S.nsuper; ++sn) {
+                    if (skip[sn]) continue;
+                    const int32_t fp = P.fwd_parent[sn];
+                    if (fp >= 0 && !skip[fp]) { fpar[sn] = fp; need[fp] += fitems[sn]; }
+                    const int32_t bp = P.bwd_wait[sn];
+                    if (bp >= 0 && !skip[bp]) bwait[sn] = bp;
+                }
+                DevCtx& cx = ph == 0 ? s->ctxA : s->ctxB;
+                cx.fwd_need = upload(s, need);
+                cx.fwd_parent = upload(s, fpar);
+                cx.bwd_wait = upload(s, bwait);
+            }
+        }
         s->d_keep = const_cast<int8_t*>(upload(s, keep));
         std::vector<int32_t> top_cols;
         for (int32_t sn = 0; sn < S.nsuper; ++sn)

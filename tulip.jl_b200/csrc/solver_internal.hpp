@@ -54,7 +54,7 @@ struct tlpb200_solver {
     int8_t* d_keep = nullptr;     // [N] 1 = this rank contributes wk[q] to the all-reduce
     // sharded phases: prefix counts of the items a phase really processes (phase 0 = own subtrees, 1 = replicated top part),
     // per item list, so that launches whose whole range is skipped on this rank are not issued at all
-    enum WorkList { WL_SMALL = 0, WL_PIECE, WL_PANEL, WL_EXT, WL_LAZY, WL_FWD, WL_BWD, WL_FBIG, WL_BBIG, WL_BELOW, WL_INV, WL_PACK, WL_COUNT };
+    enum WorkList { WL_SMALL = 0, WL_PIECE, WL_PANEL, WL_EXT, WL_LAZY, WL_FWD, WL_BWD, WL_FBIG, WL_BBIG, WL_BELOW, WL_INV, WL_PACK, WL_BSEQ, WL_COUNT };
     std::vector<int32_t> work_prefix[2][WL_COUNT];
     // in-library collectives (tlpb200_comm_init): NCCL on the solver's stream, so that a sharded update!/solve! is ONE
     // stream-ordered (graph-captured) sequence without host synchronisation between its phases
