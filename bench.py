@@ -391,9 +391,12 @@ def gpu_arm(args):
     del a, b
 
     def traffic_of(name):
+        """DRAM bytes per launch from the committed ncu --set full capture -- only when it was taken on THIS config (a launch of
+        another config moves a different amount of data); null otherwise"""
         tp = os.path.join(ROOT, "profiles", name)
         try:
-            return json.load(open(tp)).get("dram_bytes_per_launch")
+            d = json.load(open(tp))
+            return d.get("dram_bytes_per_launch") if str(d.get("config")) == cfg else None
         except Exception:
             return None
 
@@ -430,6 +433,10 @@ def gpu_arm(args):
                     "algorithmic_flops_per_step": sp["flops_update_oz"], "tasks_per_step": sp["oz_tasks"],
                     "share_of_update_ms": round(ms_oz / ms_fac, 3),
                     "note": "CUDA-event bracket around every launch of the class, kernels serialised (profiling mode)"}
+        if roofline["traffic"] is None:
+            roofline["traffic_note"] = ("no ncu --set full capture at this config's launch size (kernel replay would have to save / restore "
+                                        "the 145 GB working set); captures of the same kernels on smaller configs: profiles/r01_k_oz_update2_ncu.md "
+                                        "(128x128 two-pass tiles: 1.67x the algorithmic DRAM bytes), profiles/r01_k_oz_update_ncu.md (1.07x)")
     else:
         roofline = roofline_dmma
     ms_tri = sum(cls[k][0] for k in ("fwd_small", "fwd_large", "bwd_large", "bwd_small", "fwd_big", "bwd_big"))
