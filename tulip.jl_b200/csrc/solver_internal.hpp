@@ -39,6 +39,7 @@ struct tlpb200_solver {
     cudaStream_t aux_stream = nullptr;        // non-critical part of the chain kernels (TLPB200_SPLIT_CHAIN)
     bool split_chain = true;
     cudaEvent_t ev_pack = nullptr;
+    std::vector<cudaEvent_t> ev_stage;   // one event per 256 KiB chunk of a device -> host result copy (pipelined staging)
     int pack_slice = 96;          // TLPB200_PACK_SLICE: repack tiles issued per level from the split level on
     double pack_split = 0.0;      // TLPB200_PACK_SPLIT: level fraction from which invert/repack slices are issued early (0 = off:
                                   // measured no gain on cfg2 -- the slices queue behind the 250 us diagonal-block inversions)
