@@ -356,10 +356,6 @@ __global__ void __launch_bounds__(SL_THREADS, 1) k_fwd_large(DevCtx c, int32_t b
         }
         double t[32];
         double acc = 0.0;
-        // merged levels: the right-hand side of this supernode's columns is final once every item of its children inside
-        // this launch has finished (children outside the launch finished before it started)
-        if (merged && I.kind == 0 && c.fwd_need[s] > 0) wait_count(c.dep_cnt + s, c.fwd_need[s], c.info);
-        const double bown = (I.kind == 0 && tid < SBLK && rvalid) ? __ldcg(c.wk + f + I.r0 + tid) : 0.0;   // off the chain
         auto load_tile = [&](int j) {
             const int32_t nbj = min(SBLK, nc - j * SBLK);
             const double* col = panel + (int64_t)(j * SBLK + cg * 32) * ld + prow;
@@ -378,6 +374,11 @@ __global__ void __launch_bounds__(SL_THREADS, 1) k_fwd_large(DevCtx c, int32_t b
         }
         red[cg * SBLK + r] = acc;
         __syncthreads();
+        // merged levels: the right-hand side of this supernode's columns is final once every item of its children inside
+        // this launch has finished (children outside the launch finished before it started).  It is only consumed here, after
+        // the tiles of the earlier blocks of the same supernode: for all but a supernode's first block the wait is off the chain.
+        if (merged && I.kind == 0 && c.fwd_need[s] > 0) wait_count(c.dep_cnt + s, c.fwd_need[s], c.info);
+        const double bown = (I.kind == 0 && tid < SBLK && rvalid) ? __ldcg(c.wk + f + I.r0 + tid) : 0.0;
         if (I.kind == 1) {
             if (tid < SBLK && rvalid) {
                 const double v = red[r] + red[SBLK + r] + red[2 * SBLK + r] + red[3 * SBLK + r];
@@ -467,9 +468,9 @@ __global__ void __launch_bounds__(SL_THREADS, 1) k_bwd_large(DevCtx c, int32_t b
         const SolveItem I = merged ? c.bwd_seq[it] : c.bwd_items[it];
         const int32_t s = I.sn;
         if (c.skip && c.skip[s]) continue;
-        // merged levels: x of every ancestor is final once all items of the in-launch parent have finished
-        if (merged && c.bwd_wait[s] >= 0) wait_count(c.dep_cnt + c.nsuper + c.bwd_wait[s], c.bwd_nitems[c.bwd_wait[s]], c.info);
         if (merged && I.kind == 2) {
+            // merged levels: x of every ancestor is final once all items of the in-launch parent have finished
+            if (c.bwd_wait[s] >= 0) wait_count(c.dep_cnt + c.nsuper + c.bwd_wait[s], c.bwd_nitems[c.bwd_wait[s]], c.info);
             // rows below the columns of a tall supernode (what k_bwd_below does in the per-level path): accumulate into bacc,
             // then tell the supernode's block items that one more below item is in place
             bwd_below_item(c, s, I.blk, I.r0, I.nr, red);
@@ -478,7 +479,6 @@ __global__ void __launch_bounds__(SL_THREADS, 1) k_bwd_large(DevCtx c, int32_t b
             if (tid == 0) atomicAdd(c.dep_cnt + 2 * c.nsuper + s, 1);
             continue;
         }
-        if (merged && c.bwd_nbelow[s] > 0) wait_count(c.dep_cnt + 2 * c.nsuper + s, c.bwd_nbelow[s], c.info);
         const int32_t f = c.sn_first[s];
         const int32_t nc = c.sn_first[s + 1] - f;
         const int64_t rp = c.sn_rowptr[s];
@@ -499,6 +499,11 @@ __global__ void __launch_bounds__(SL_THREADS, 1) k_bwd_large(DevCtx c, int32_t b
             bown = __ldcg(c.wk + f + i * SBLK + tid);
             sown = (double)c.sign[f + i * SBLK + tid];
         }
+        // merged levels: x of every ancestor is final once all items of the in-launch parent have finished, and this
+        // supernode's below items (kind 2) have accumulated into bacc -- waited for here, after the prefetch of the inverse
+        // diagonal block and the own right-hand side have been issued
+        if (merged && c.bwd_wait[s] >= 0) wait_count(c.dep_cnt + c.nsuper + c.bwd_wait[s], c.bwd_nitems[c.bwd_wait[s]], c.info);
+        if (merged && c.bwd_nbelow[s] > 0) wait_count(c.dep_cnt + 2 * c.nsuper + s, c.bwd_nbelow[s], c.info);
         // p[cc] accumulates sum_r L[r, i*128 + cg*32 + cc] * x[r] over this thread's rows r (mod 128)
         double p[32];
 #pragma unroll
