@@ -179,6 +179,10 @@ int tlpb200_debug_solve_ops(const tlpb200_solver* s, int64_t* counts, int32_t* f
                             int32_t* fwd_parent, int32_t* bwd_wait, int32_t* bwd_nitems, void* fwd_items, void* bwd_seq,
                             int32_t* sn_parent, int32_t* bwd_nbelow);
 
+/* sharded solver (nranks > 1): dependency targets of the merged-level sweeps inside phase 0 (own subtrees) / 1 (replicated top
+ * part) -- per-supernode int32 arrays like fwd_need / fwd_parent / bwd_wait above, restricted to supernodes of the same phase */
+int tlpb200_debug_phase_deps(const tlpb200_solver* s, int32_t phase, int32_t* fwd_need, int32_t* fwd_parent, int32_t* bwd_wait);
+
 /* ---- multi-GPU, one process per GPU (no counterpart in the reference, NEWS.md:31) -------------
  * Created with opt.nranks > 1 every rank analyses the same matrix, owns the elimination-tree subtrees
  * assigned to it (owner[s] == rank) and replicates the top part (owner[s] == -1).  The caller performs the

@@ -161,3 +161,135 @@ def test_merged_sweeps_replay(name, gen, sysname, G, ncol):
     for kind, b, e, lvl in ops["bwd_ops"]:
         if kind == 3:
             assert all(not (k2 in (0, 2) and l2 > lvl) for k2, _, _, l2 in ops["bwd_ops"][list(map(tuple, ops["bwd_ops"])).index((kind, b, e, lvl)) + 1:])
+
+
+@pytest.mark.parametrize("nranks", [2, 4])
+@pytest.mark.parametrize("G", [1, 148])
+def test_merged_sweeps_replay_inside_sharded_phases(nranks, G):
+    """N > 1: every rank walks the same merged launch sequence twice -- phase 0 on the subtrees it owns, phase 1 on the
+    replicated top part -- with per-phase dependency targets (tlpb200_debug_phase_deps).  Replay of the forward order
+    (phase 0, then phase 1) and of the backward order (phase 1, then phase 0) on every rank: no dead-lock, a supernode's
+    right-hand side is read only after ALL its children finished (in this phase or an earlier one), an ancestor's solution only
+    after it is final, and a top supernode's counter is never touched by a subtree child (it runs in another phase)."""
+    lp = lpgen.block_angular(blocks=8, mb=300, nb=600, width=64, link=200, name="b")
+    for rank in range(nranks):
+        k = pkg.setup(lp.A, pkg.K1(), pkg.Backend(analyze_only=True, rank=rank, nranks=nranks))
+        ops = k.solve_ops()
+        owner, _, _ = k.dist_info()
+        sym = k.symbolic()
+        first = sym["sn_first"]
+        ns = len(first) - 1
+        par = ops["sn_parent"]
+        fit, bit = ops["fwd_items"], ops["bwd_seq"]
+        small_list = k.update_plan()["small_list"]
+        bp = k.big_plan()
+        ncb = lambda s: (first[s + 1] - first[s] + 127) // 128
+        children = [[] for _ in range(ns)]
+        for s in range(ns):
+            if par[s] >= 0:
+                children[par[s]].append(s)
+        live = [owner == rank, owner == -1]
+        assert live[0].any() and live[1].any()
+        n_items = np.bincount(fit["sn"], minlength=ns)
+        # ---- forward: phase 0 then phase 1 ------------------------------------------------------------------------
+        done_sn = np.zeros(ns, bool)
+        cnt = np.zeros(ns, int)
+        fin = np.zeros(ns, int)
+        flag = {}
+        for ph in (0, 1):
+            need, fpar, _ = k.phase_deps(ph)
+            assert np.all(need[~live[ph]] == 0) and np.all(fpar[~live[ph]] == -1)
+            for kind, b, e, lvl in ops["fwd_ops"]:
+                if kind == 0:
+                    for s in small_list[b:e]:
+                        if live[ph][s]:
+                            assert all(done_sn[c] for c in children[s] if owner[c] in (rank, -1))
+                            done_sn[s] = True
+                    continue
+                if kind == 2:
+                    for s in np.unique(bp["fwd"]["sn"][b:e]):
+                        if live[ph][s]:
+                            assert all(done_sn[c] for c in children[s] if owner[c] in (rank, -1))
+                            done_sn[s] = True
+                    continue
+
+                def ready(x):
+                    it = fit[x]; s = int(it["sn"])
+                    if not live[ph][s]:
+                        return True                      # skipped item: `continue`
+                    if it["kind"] == 0:
+                        return cnt[s] >= need[s] and all(flag.get((s, j), False) for j in range(int(it["blk"])))
+                    return all(flag.get((s, j), False) for j in range(ncb(s)))
+
+                def done(x):
+                    it = fit[x]; s = int(it["sn"])
+                    if not live[ph][s]:
+                        return
+                    if it["kind"] == 0:
+                        for c in children[s]:
+                            if owner[c] in (rank, -1):      # children owned by other ranks arrive through the all-reduce
+                                assert done_sn[c] or fin[c] == n_items[c] > 0, ("rhs read before child finished", ph, s, c)
+                        flag[(s, int(it["blk"]))] = True
+                    fin[s] += 1
+                    if fpar[s] >= 0:
+                        assert live[ph][fpar[s]], "notification across phases"
+                        cnt[fpar[s]] += 1
+                assert _replay(fit, b, e, G, ready, done), f"forward dead-lock, rank {rank} phase {ph}"
+                for x in range(b, e):
+                    s = fit[x]["sn"]
+                    if live[ph][s] and fin[s] == n_items[s]:
+                        done_sn[s] = True
+        assert np.all(done_sn[(owner == rank) | (owner == -1)])
+        # ---- backward: phase 1 (top) then phase 0 (own subtrees) ---------------------------------------------------------
+        bdone = np.zeros(ns, int)
+        bdone_sn = np.zeros(ns, bool)
+        below_done = np.zeros(ns, int)
+        bflag = {}
+        for ph in (1, 0):
+            _, _, bwait = k.phase_deps(ph)
+            for kind, b, e, lvl in ops["bwd_ops"]:
+                if kind == 3:
+                    continue
+                if kind == 0:
+                    for s in small_list[b:e]:
+                        if live[ph][s]:
+                            assert par[s] < 0 or bdone_sn[par[s]]
+                            bdone_sn[s] = True
+                    continue
+                if kind == 2:
+                    for s in np.unique(bp["bwd"]["sn"][b:e]):
+                        if live[ph][s]:
+                            assert par[s] < 0 or bdone_sn[par[s]]
+                            bdone_sn[s] = True
+                    continue
+
+                def ready(x):
+                    it = bit[x]; s = int(it["sn"])
+                    if not live[ph][s]:
+                        return True
+                    w = bwait[s]
+                    if w >= 0 and bdone[w] < ops["bwd_nitems"][w]:
+                        return False
+                    if it["kind"] == 2:
+                        return True
+                    if below_done[s] < ops["bwd_nbelow"][s]:
+                        return False
+                    return all(bflag.get((s, j), False) for j in range(int(it["blk"]) + 1, ncb(s)))
+
+                def done(x):
+                    it = bit[x]; s = int(it["sn"])
+                    if not live[ph][s]:
+                        return
+                    p = par[s]
+                    assert p < 0 or bdone_sn[p] or (ops["bwd_nitems"][p] > 0 and bdone[p] == ops["bwd_nitems"][p]), ("ancestor read early", ph, s, p)
+                    if it["kind"] == 2:
+                        below_done[s] += 1
+                        return
+                    bflag[(s, int(it["blk"]))] = True
+                    bdone[s] += 1
+                assert _replay(bit, b, e, G, ready, done), f"backward dead-lock, rank {rank} phase {ph}"
+                for x in range(b, e):
+                    s = bit[x]["sn"]
+                    if live[ph][s] and bdone[s] == ops["bwd_nitems"][s]:
+                        bdone_sn[s] = True
+        assert np.all(bdone_sn[(owner == rank) | (owner == -1)])

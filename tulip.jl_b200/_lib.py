@@ -82,7 +82,7 @@ SYMBOLS = [
     "tlpb200_backend_name", "tlpb200_linear_system", "tlpb200_destroy",
     "tlpb200_dist_info", "tlpb200_update_begin", "tlpb200_top_panels", "tlpb200_update_end",
     "tlpb200_solve_begin", "tlpb200_work_vector", "tlpb200_solve_mid", "tlpb200_solve_end",
-    "tlpb200_get_dense_cols", "tlpb200_debug_big_plan", "tlpb200_debug_chain_times", "tlpb200_debug_factor_trace", "tlpb200_debug_ozaki", "tlpb200_debug_update_plan", "tlpb200_abi_sizes", "tlpb200_debug_solve_ops",
+    "tlpb200_get_dense_cols", "tlpb200_debug_big_plan", "tlpb200_debug_chain_times", "tlpb200_debug_factor_trace", "tlpb200_debug_ozaki", "tlpb200_debug_update_plan", "tlpb200_abi_sizes", "tlpb200_debug_solve_ops", "tlpb200_debug_phase_deps",
 ]
 
 _lib = None
@@ -159,6 +159,8 @@ def load():
     lib.tlpb200_debug_factor_trace.restype = C.c_int
     lib.tlpb200_debug_solve_ops.argtypes = [p, C.POINTER(C.c_int64), p, p, p, p, p, p, p, p, p, p]
     lib.tlpb200_debug_solve_ops.restype = C.c_int
+    lib.tlpb200_debug_phase_deps.argtypes = [p, C.c_int32, p, p, p]
+    lib.tlpb200_debug_phase_deps.restype = C.c_int
     lib.tlpb200_abi_sizes.argtypes = [C.POINTER(C.c_int32)]
     lib.tlpb200_abi_sizes.restype = None
     lib.tlpb200_debug_update_plan.argtypes = [p, C.POINTER(C.c_int64), p, p, p, p, p, p, p, p, p]

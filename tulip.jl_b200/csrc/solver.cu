@@ -214,6 +214,30 @@ inline bool has_work(const tlpb200_solver* s, int wl, int64_t begin, int64_t end
     return pre[(size_t)end] - pre[(size_t)begin] > 0;
 }
 
+// Merged-level sweeps inside a sharded phase (phase 0 = own subtrees, 1 = replicated top part): a supernode only waits for /
+// notifies supernodes that run in the SAME phase.  A subtree root's parent belongs to the top part: in the forward sweep it
+// runs in a later phase (no notification: its counter must only see top children), in the backward sweep it is complete
+// before the phase starts (no wait).
+void build_phase_deps(tlpb200_solver* s) {
+    const Plan& P = s->plan;
+    const int32_t ns = s->sym.nsuper;
+    std::vector<int32_t> fitems(ns, 0);
+    for (const SolveItem& it : P.fwd_items) fitems[it.sn]++;
+    for (int ph = 0; ph < 2; ++ph) {
+        auto live = [&](int32_t sn) { return ph == 0 ? (s->owner[sn] == s->rank) : (s->owner[sn] == -1); };
+        s->phase_need[ph].assign(ns, 0);
+        s->phase_fpar[ph].assign(ns, -1);
+        s->phase_bwait[ph].assign(ns, -1);
+        for (int32_t sn = 0; sn < ns; ++sn) {
+            if (!live(sn)) continue;
+            const int32_t fp = P.fwd_parent[sn];
+            if (fp >= 0 && live(fp)) { s->phase_fpar[ph][sn] = fp; s->phase_need[ph][fp] += fitems[sn]; }
+            const int32_t bp = P.bwd_wait[sn];
+            if (bp >= 0 && live(bp)) s->phase_bwait[ph][sn] = bp;
+        }
+    }
+}
+
 void build_work_prefix(tlpb200_solver* s) {
     const Plan& P = s->plan;
     for (int ph = 0; ph < 2; ++ph) {
@@ -917,29 +941,13 @@ void setup_device(tlpb200_solver* s) {
         }
         s->ctxA = s->ctx; s->ctxA.skip = upload(s, skipA);
         s->ctxB = s->ctx; s->ctxB.skip = upload(s, skipB);
-        // merged-level sweeps inside a phase: a supernode only waits for / notifies supernodes that run in the SAME phase (a
-        // subtree root's parent belongs to the top part: in the forward sweep it runs in a later phase, in the backward sweep
-        // it is complete before the phase starts)
-        {
-            std::vector<int32_t> fitems(S.nsuper, 0);
-            for (const SolveItem& it : P.fwd_items) fitems[it.sn]++;
-            for (int ph = 0; ph < 2; ++ph) {
-                const std::vector<int8_t>& skip = ph == 0 ? skipA : skipB;
-                std::vector<int32_t> need(S.nsuper, 0), fpar(S.nsuper, -1), bwait(S.nsuper, -1);
-                for (int32_t sn = 0; sn < S.nsuper; ++sn) {
-                    if (skip[sn]) continue;
-                    const int32_t fp = P.fwd_parent[sn];
-                    if (fp >= 0 && !skip[fp]) { fpar[sn] = fp; need[fp] += fitems[sn]; }
-                    const int32_t bp = P.bwd_wait[sn];
-                    if (bp >= 0 && !skip[bp]) bwait[sn] = bp;
-                }
-                DevCtx& cx = ph == 0 ? s->ctxA : s->ctxB;
-                cx.fwd_need = upload(s, need);
-                cx.fwd_parent = upload(s, fpar);
-                cx.bwd_wait = upload(s, bwait);
-            }
+        // merged-level sweeps inside a phase: per-phase dependency targets (build_phase_deps, host)
+        for (int ph = 0; ph < 2; ++ph) {
+            DevCtx& cx = ph == 0 ? s->ctxA : s->ctxB;
+            cx.fwd_need = upload(s, s->phase_need[ph]);
+            cx.fwd_parent = upload(s, s->phase_fpar[ph]);
+            cx.bwd_wait = upload(s, s->phase_bwait[ph]);
         }
-        s->d_keep = const_cast<int8_t*>(upload(s, keep));
         std::vector<int32_t> top_cols;
         for (int32_t sn = 0; sn < S.nsuper; ++sn)
             if (s->owner[sn] == -1)
@@ -1207,7 +1215,7 @@ int tlpb200_create(tlpb200_solver** out, int64_t m, int64_t n, const int64_t* co
         if (const char* e = getenv("TLPB200_OZAKI_TILE")) po.oz_tile_n = atoi(e) == 128 ? 128 : (atoi(e) == 64 ? 64 : 0);
         if (const char* e = getenv("TLPB200_OZAKI_KSPLIT")) po.oz_ksplit = std::max(32, (atoi(e) / 32) * 32);
         build_plan(s->sym, po, s->plan);
-        if (s->nranks > 1) build_work_prefix(s);
+        if (s->nranks > 1) { build_work_prefix(s); build_phase_deps(s); }
         lap("build_plan");
         if (system == TLPB200_K1)
             build_assembly_k1(s->sym, m, n, cp_f, ri_f, va_f, s->maps);
@@ -1617,6 +1625,17 @@ int tlpb200_debug_solve_ops(const tlpb200_solver* s, int64_t* counts, int32_t* f
     cp(bwd_seq, P.bwd_seq.data(), P.bwd_seq.size() * sizeof(SolveItem));
     cp(sn_parent, s->sym.sn_parent.data(), s->sym.sn_parent.size() * 4);
     cp(bwd_nbelow, P.bwd_nbelow.data(), P.bwd_nbelow.size() * 4);
+    return TLPB200_OK;
+}
+
+// per-phase dependency targets of the merged-level sweeps of a sharded solver (host data; phase 0 = own subtrees, 1 = top part)
+int tlpb200_debug_phase_deps(const tlpb200_solver* s, int32_t phase, int32_t* fwd_need, int32_t* fwd_parent, int32_t* bwd_wait) {
+    if (!s || phase < 0 || phase > 1) return TLPB200_BAD_ARG;
+    if (s->nranks < 2) return TLPB200_BAD_ARG;
+    auto cp = [](int32_t* dst, const std::vector<int32_t>& v) { if (dst && !v.empty()) std::memcpy(dst, v.data(), v.size() * 4); };
+    cp(fwd_need, s->phase_need[phase]);
+    cp(fwd_parent, s->phase_fpar[phase]);
+    cp(bwd_wait, s->phase_bwait[phase]);
     return TLPB200_OK;
 }
 

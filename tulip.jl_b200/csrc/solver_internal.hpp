@@ -57,6 +57,7 @@ struct tlpb200_solver {
     // per item list, so that launches whose whole range is skipped on this rank are not issued at all
     enum WorkList { WL_SMALL = 0, WL_PIECE, WL_PANEL, WL_EXT, WL_LAZY, WL_FWD, WL_BWD, WL_FBIG, WL_BBIG, WL_BELOW, WL_INV, WL_PACK, WL_BSEQ, WL_COUNT };
     std::vector<int32_t> work_prefix[2][WL_COUNT];
+    std::vector<int32_t> phase_need[2], phase_fpar[2], phase_bwait[2];   // merged-level sweeps: per-phase dependency targets
     // in-library collectives (tlpb200_comm_init): NCCL on the solver's stream, so that a sharded update!/solve! is ONE
     // stream-ordered (graph-captured) sequence without host synchronisation between its phases
     ncclComm_t comm = nullptr;

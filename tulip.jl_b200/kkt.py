@@ -361,6 +361,16 @@ class B200KKTSolver:
         return dict(fwd_ops=fo, bwd_ops=bo, fwd_need=need, fwd_parent=fpar, bwd_wait=bwait, bwd_nitems=bn, fwd_items=fit,
                     bwd_seq=bit, sn_parent=par, bwd_nbelow=nbel)
 
+    def phase_deps(self, phase):
+        """sharded solver: (fwd_need, fwd_parent, bwd_wait) of the merged-level sweeps inside phase 0 (own subtrees) / 1 (top)"""
+        ns = self.stats()["nsuper"]
+        need = np.zeros(ns, np.int32); fpar = np.full(ns, -1, np.int32); bwait = np.full(ns, -1, np.int32)
+        vp = lambda a: C.c_void_p(a.ctypes.data)
+        rc = _lib.load().tlpb200_debug_phase_deps(self._h, phase, vp(need), vp(fpar), vp(bwait))
+        if rc != _lib.OK:
+            _raise(rc, self._h)
+        return need, fpar, bwait
+
     def big_plan(self):
         """Dense-solve plan of the big supernodes (host data, available on analyze_only handles)."""
         lib = _lib.load()
