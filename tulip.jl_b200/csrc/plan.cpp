@@ -742,19 +742,23 @@ void partition_subtrees(const Symbolic& S, int nranks, std::vector<int32_t>& own
 
 // Panel storage order: supernodes of the subtrees first, the replicated top part last (so that the
 // top panels form one contiguous range for the all-reduce).  Recomputes sn_xptr and diagpos.
-int64_t relayout_panels(Symbolic& S, const std::vector<int32_t>& owner) {
+int64_t relayout_panels(Symbolic& S, const std::vector<int32_t>& owner, int32_t nranks, std::vector<int64_t>* rank_begin) {
     const int32_t ns = S.nsuper;
     int64_t off = 0, top_begin = 0;
-    for (int pass = 0; pass < 2; ++pass) {
-        if (pass == 1) top_begin = off;
+    if (rank_begin) rank_begin->assign((size_t)nranks + 1, 0);
+    // panels grouped by owner: [rank 0 | rank 1 | ... | replicated top part], so that a rank clears / touches one contiguous range
+    for (int32_t pass = 0; pass <= nranks; ++pass) {
+        if (pass == nranks) top_begin = off;
+        if (rank_begin && pass < nranks) (*rank_begin)[pass] = off;
         for (int32_t s = 0; s < ns; ++s) {
-            if ((owner[s] < 0) != (pass == 1)) continue;
+            if (pass < nranks ? (owner[s] != pass) : (owner[s] >= 0)) continue;
             const int64_t ncol = S.sn_first[s + 1] - S.sn_first[s];
             const int64_t nrow = S.sn_rowptr[s + 1] - S.sn_rowptr[s];
             S.sn_xptr[s] = off;
             off += nrow * ncol;
         }
     }
+    if (rank_begin) (*rank_begin)[nranks] = top_begin;
     S.sn_xptr[ns] = off;     // == lx_size (the last entry is no longer "end of supernode ns-1")
     for (int32_t s = 0; s < ns; ++s) {
         const int64_t nrow = S.sn_rowptr[s + 1] - S.sn_rowptr[s];

@@ -217,7 +217,7 @@ void build_assembly_k2(const Symbolic& S, int64_t m, int64_t n, const int64_t* c
 
 // multi-GPU sharding of independent elimination-tree subtrees (see plan.cpp)
 void partition_subtrees(const Symbolic& S, int nranks, std::vector<int32_t>& owner, std::vector<double>* rank_work = nullptr);
-int64_t relayout_panels(Symbolic& S, const std::vector<int32_t>& owner);   // returns the offset of the top part in Lx
+int64_t relayout_panels(Symbolic& S, const std::vector<int32_t>& owner, int32_t nranks, std::vector<int64_t>* rank_begin = nullptr);   // returns the offset of the top part in Lx
 
 // position of permuted entry (row gi, column gk), gi >= gk, inside Lx
 int64_t lx_position(const Symbolic& S, int32_t gi, int32_t gk);

@@ -264,10 +264,17 @@ void build_work_prefix(tlpb200_solver* s) {
 }
 
 // ---- the numeric phases, enqueued on s->stream; `count` accumulates kernel launches -------------
-void enqueue_assemble(tlpb200_solver* s, int64_t& count) {
+void enqueue_assemble(tlpb200_solver* s, int64_t& count, bool own_panels_only = false) {
     cudaStream_t st = s->stream;
     Scope sc(s, 0);
-    CK(cudaMemsetAsync(s->ctx.Lx, 0, (size_t)s->sym.lx_size * sizeof(double), st));
+    if (own_panels_only && s->nranks > 1 && s->rank_begin.size() == (size_t)s->nranks + 1) {
+        // sharded: only this rank's subtrees and the top part are ever read here (panels are grouped by owner)
+        const int64_t b = s->rank_begin[s->rank], e = s->rank_begin[s->rank + 1];
+        if (e > b) CK(cudaMemsetAsync(s->ctx.Lx + b, 0, (size_t)(e - b) * sizeof(double), st));
+        if (s->sym.lx_size > s->top_begin) CK(cudaMemsetAsync(s->ctx.Lx + s->top_begin, 0, (size_t)(s->sym.lx_size - s->top_begin) * sizeof(double), st));
+    } else {
+        CK(cudaMemsetAsync(s->ctx.Lx, 0, (size_t)s->sym.lx_size * sizeof(double), st));
+    }
     CK(cudaMemsetAsync(s->ctx.info, 0x7f, sizeof(int32_t), st));
     CK(cudaMemsetAsync(s->lazy_ctr, 0, (2 * s->plan.levels.size() + 2) * sizeof(int32_t), st));
     if (s->ctx.trace_min) {
@@ -618,7 +625,7 @@ void enqueue_update_all(tlpb200_solver* s, int64_t& cnt) {
     const NcclApi& api = nccl_api();
     const int64_t top_cnt = s->sym.lx_size - s->top_begin;
     s->cur = &s->ctx;
-    enqueue_assemble(s, cnt);
+    enqueue_assemble(s, cnt, true);
     // original entries of the replicated top part are contributed by rank 0 only
     if (s->rank != 0 && top_cnt > 0) CK(cudaMemsetAsync(s->ctx.Lx + s->top_begin, 0, (size_t)top_cnt * 8, s->stream));
     s->cur = &s->ctxA;
@@ -1204,7 +1211,7 @@ int tlpb200_create(tlpb200_solver** out, int64_t m, int64_t n, const int64_t* co
         s->nranks = std::max(1, s->opt.nranks);
         if (s->rank < 0 || s->rank >= s->nranks) throw std::invalid_argument("rank out of range");
         partition_subtrees(s->sym, s->nranks, s->owner);
-        if (s->nranks > 1) s->top_begin = relayout_panels(s->sym, s->owner);
+        if (s->nranks > 1) s->top_begin = relayout_panels(s->sym, s->owner, s->nranks, &s->rank_begin);
         PlanOptions po;
         po.small_elems = s->opt.small_elems;
         if (s->opt.dense_solve_ncol > 0) po.big_ncol = s->opt.dense_solve_ncol;

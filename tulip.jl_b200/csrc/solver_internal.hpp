@@ -52,6 +52,7 @@ struct tlpb200_solver {
     int rank = 0, nranks = 1;
     std::vector<int32_t> owner;   // [nsuper] rank owning each supernode, -1 = replicated top part
     int64_t top_begin = 0;        // offset of the top panels inside Lx
+    std::vector<int64_t> rank_begin;   // [nranks + 1] panels are grouped by owner: rank r owns Lx[rank_begin[r], rank_begin[r + 1])
     int8_t* d_keep = nullptr;     // [N] 1 = this rank contributes wk[q] to the all-reduce
     // sharded phases: prefix counts of the items a phase really processes (phase 0 = own subtrees, 1 = replicated top part),
     // per item list, so that launches whose whole range is skipped on this rank are not issued at all
