@@ -955,6 +955,7 @@ void setup_device(tlpb200_solver* s) {
             cx.fwd_parent = upload(s, s->phase_fpar[ph]);
             cx.bwd_wait = upload(s, s->phase_bwait[ph]);
         }
+        s->d_keep = const_cast<int8_t*>(upload(s, keep));
         std::vector<int32_t> top_cols;
         for (int32_t sn = 0; sn < S.nsuper; ++sn)
             if (s->owner[sn] == -1)
