@@ -657,6 +657,8 @@ void enqueue_solve_all(tlpb200_solver* s, const double* xip, const double* xid, 
         return;
     }
     const NcclApi& api = nccl_api();
+    if (!s->d_keep || !s->ctxA.skip || !s->ctxB.skip || (s->ntop > 0 && (!s->d_top_cols || !s->d_tbuf)))
+        throw std::runtime_error("sharded solver: device state of the phases is incomplete");
     s->cur = &s->ctx;
     enqueue_rhs(s, xip, xid, cnt);
     launch_zero_unowned(s->ctx, s->d_keep, s->stream);
