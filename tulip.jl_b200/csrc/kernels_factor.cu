@@ -11,6 +11,8 @@
 // scripts/dmma_bench.cu); every mma.sync f64 shape lowers to DMMA.8x8x4.  tcgen05 has no FP64 kind.
 #include "kernels.cuh"
 
+#include <cstdlib>
+
 namespace tlp {
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
@@ -215,6 +217,206 @@ __global__ void __launch_bounds__(DF_THREADS, 1) k_diag_factor(DevCtx c, int32_t
 }
 
 // ------------------------------------------------------------------------------------------
+// k_diag_factor2 (round 2): same elimination (unscaled columns u_ij, signed pivots d_j, W = U D^-1) reorganised around the
+// two things that bound a 128-column block on one SM:
+//  * the pivot chain.  Every thread of the panel warps carries a private copy of the 8x8 diagonal block in registers and
+//    eliminates it redundantly next to its own row: no shuffle, no shared-memory hand-over and no block-wide barrier between
+//    the diagonal block and the rows below it -- per column the chain is one reciprocal and two FMAs.
+//  * the FP64 pipe.  The trailing update C -= U W' runs on DMMA 8x8x4 tiles straight out of shared memory (two k-steps per
+//    8-column block).  With look-ahead the tiles of the NEXT 8 columns are updated first by all warps; then warps 0-3
+//    eliminate that block while the other warps finish the rest of the trailing matrix underneath.
+// Layout: Cs column-major [128][130] (130: conflict-free accumulator fragments), U / -W panels [2][8][132] double-buffered.
+// ------------------------------------------------------------------------------------------
+constexpr int DF2_THREADS = 384;
+constexpr int DF2_WARPS = DF2_THREADS / 32;
+constexpr int DF2_PANEL_WARPS = 4;
+constexpr int LDC2 = PIECE + 2;
+constexpr int LDP2 = PIECE + 4;
+
+// rows j0 + t (t = thread index inside the panel warps) of the 8 columns j0 .. j0+7
+__device__ __forceinline__ void df2_panel(double* Cs, double* Up, double* Wn, double* dd, double* rdd, const double* sgn,
+                                          int32_t gcol0, int32_t* info, int j0, int nb, int nrows, int t) {
+    const bool live = t < nrows;
+    const int i = j0 + (live ? t : 0);
+    double g[NBD][NBD];     // private copy of the diagonal block (lower part)
+    double u[NBD], rr[NBD];
+#pragma unroll
+    for (int j = 0; j < NBD; ++j) {
+#pragma unroll
+        for (int k = j; k < NBD; ++k) g[k][j] = Cs[(j0 + j) * LDC2 + j0 + k];
+        u[j] = Cs[(j0 + j) * LDC2 + i];
+    }
+    // the threads of the diagonal rows write their eliminated entries back over the block every other thread has just read
+    asm volatile("bar.sync 1, %0;" ::"n"(DF2_PANEL_WARPS * 32) : "memory");
+    if (!live) return;
+#pragma unroll
+    for (int j = 0; j < NBD; ++j) {
+        double d = g[j][j];
+        const double sj = sgn[j0 + j];
+        if (!(d * sj > 0.0)) {
+            if (t == j && j < nb) atomicMin(info, gcol0 + j0 + j);
+            d = sj;
+        }
+        const double r = 1.0 / d;
+        rr[j] = r;
+        if (t == j) { dd[j0 + j] = d; rdd[j0 + j] = r; }
+        double m[NBD];
+#pragma unroll
+        for (int l = j + 1; l < NBD; ++l) m[l] = g[l][j] * r;
+#pragma unroll
+        for (int k = j + 1; k < NBD; ++k)
+#pragma unroll
+            for (int l = j + 1; l <= k; ++l) g[k][l] -= g[k][j] * m[l];
+        const double a = u[j];
+#pragma unroll
+        for (int l = j + 1; l < NBD; ++l) u[l] -= a * m[l];
+    }
+    if (t < NBD) {
+#pragma unroll
+        for (int j = 0; j < NBD; ++j)
+            if (j <= t) Cs[(j0 + j) * LDC2 + i] = u[j];
+    } else {
+#pragma unroll
+        for (int j = 0; j < NBD; ++j) {
+            Cs[(j0 + j) * LDC2 + i] = u[j];
+            Up[j * LDP2 + i] = u[j];
+            Wn[j * LDP2 + i] = -u[j] * rr[j];
+        }
+    }
+}
+
+// C[8ti.., 8tk..] += U[8ti.., :] * Wn[8tk.., :]'   (one 8x8 tile, K = 8)
+__device__ __forceinline__ void df2_tile2(double* Cs, const double* Up, const double* Wn, int tiA, int tkA, int tiB, int tkB, bool hasB,
+                                          int g, int t4) {
+    const double a0 = Up[t4 * LDP2 + 8 * tiA + g], a1 = Up[(4 + t4) * LDP2 + 8 * tiA + g];
+    const double b0 = Wn[t4 * LDP2 + 8 * tkA + g], b1 = Wn[(4 + t4) * LDP2 + 8 * tkA + g];
+    const double e0 = Up[t4 * LDP2 + 8 * tiB + g], e1 = Up[(4 + t4) * LDP2 + 8 * tiB + g];
+    const double f0 = Wn[t4 * LDP2 + 8 * tkB + g], f1 = Wn[(4 + t4) * LDP2 + 8 * tkB + g];
+    double* pa = Cs + (8 * tkA + 2 * t4) * LDC2 + 8 * tiA + g;
+    double* pb = Cs + (8 * tkB + 2 * t4) * LDC2 + 8 * tiB + g;
+    double c0 = pa[0], c1 = pa[LDC2];
+    double h0 = pb[0], h1 = pb[LDC2];
+    dmma884(c0, c1, a0, b0);
+    dmma884(h0, h1, e0, f0);
+    dmma884(c0, c1, a1, b1);
+    dmma884(h0, h1, e1, f1);
+    pa[0] = c0;
+    pa[LDC2] = c1;
+    if (hasB) {
+        pb[0] = h0;
+        pb[LDC2] = h1;
+    }
+}
+
+// t-th tile (row-major over the lower triangle p >= q >= 0)
+__device__ __forceinline__ void df2_tri(int t, int& p, int& q) {
+    p = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+    while (p * (p + 1) / 2 > t) --p;
+    while ((p + 1) * (p + 2) / 2 <= t) ++p;
+    q = t - p * (p + 1) / 2;
+}
+
+template <bool LOOKAHEAD>
+__global__ void __launch_bounds__(DF2_THREADS, 1) k_diag_factor2(DevCtx c, int32_t begin) {
+    extern __shared__ double smem_d[];
+    double* Cs = smem_d;                       // [PIECE][LDC2] column-major
+    double* Upan = Cs + PIECE * LDC2;          // [2][NBD][LDP2]  u_ij of the current block
+    double* Wpan = Upan + 2 * NBD * LDP2;      // [2][NBD][LDP2]  -u_ij / d_j
+    double* dd = Wpan + 2 * NBD * LDP2;        // [PIECE] pivots
+    double* rdd = dd + PIECE;                  // [PIECE] reciprocals (later: 1 / (s_j l_jj))
+    double* sgn = rdd + PIECE;                 // [PIECE] expected pivot signs
+    const Piece pc = c.pieces[c.level_pieces[begin + blockIdx.x]];
+    const int32_t s = pc.sn;
+    if (c.skip && c.skip[s]) return;
+    const int32_t f = c.sn_first[s];
+    const int32_t ld = (int32_t)(c.sn_rowptr[s + 1] - c.sn_rowptr[s]);
+    const int32_t lc0 = pc.c0 - f, w = pc.c1 - pc.c0;
+    double* D = c.Lx + c.sn_xptr[s] + (int64_t)lc0 * ld + lc0;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int il = tid & (PIECE - 1), q3 = tid >> 7;      // 3 columns per pass of the block copy
+    const int nt = (w + NBD - 1) / NBD, nt8 = nt * NBD;
+
+    if (tid == 0) trace_mark(c, pc.level, 0, false);
+    if (tid < PIECE) sgn[tid] = (tid < w) ? (double)c.sign[pc.c0 + tid] : 1.0;
+    // lower triangle in, everything else of the nt8 x 128 window zero, unit diagonal on the padding columns
+    for (int kb = 0; kb < nt8; kb += 24) {
+        double v[8];
+#pragma unroll
+        for (int x = 0; x < 8; ++x) {
+            const int k = kb + q3 + 3 * x;
+            v[x] = (k < w && il < w && il >= k) ? D[(int64_t)k * ld + il] : ((k == il && k >= w) ? 1.0 : 0.0);
+        }
+#pragma unroll
+        for (int x = 0; x < 8; ++x) {
+            const int k = kb + q3 + 3 * x;
+            if (k < nt8) Cs[k * LDC2 + il] = v[x];
+        }
+    }
+    __syncthreads();
+    if (warp < DF2_PANEL_WARPS) df2_panel(Cs, Upan, Wpan, dd, rdd, sgn, pc.c0, c.info, 0, min(NBD, w), nt8, tid);
+    __syncthreads();
+    for (int b = 0; b + 1 < nt; ++b) {
+        const double* Up = Upan + (b & 1) * NBD * LDP2;
+        const double* Wn = Wpan + (b & 1) * NBD * LDP2;
+        const int t1 = b + 1;               // first trailing tile row / column
+        const int nrem = nt - t1;           // tile rows left
+        if (LOOKAHEAD) {
+            // (1) columns of the next block, all warps: tiles (t1 + x, t1)
+            for (int x = warp; x < nrem; x += 2 * DF2_WARPS) {
+                const bool hasB = x + DF2_WARPS < nrem;
+                df2_tile2(Cs, Up, Wn, t1 + x, t1, hasB ? t1 + x + DF2_WARPS : t1 + x, t1, hasB, g, t4);
+            }
+            __syncthreads();
+            // (2) panel warps eliminate the next block; the others finish the trailing matrix (tile columns >= t1 + 1)
+            if (warp < DF2_PANEL_WARPS) {
+                const int j0 = t1 * NBD;
+                df2_panel(Cs, Upan + (t1 & 1) * NBD * LDP2, Wpan + (t1 & 1) * NBD * LDP2, dd, rdd, sgn, pc.c0, c.info, j0, min(NBD, w - j0),
+                          nt8 - j0, tid);
+            } else {
+                constexpr int NW = DF2_WARPS - DF2_PANEL_WARPS;
+                const int T = nrem - 1, ntile = T * (T + 1) / 2, wq = warp - DF2_PANEL_WARPS;
+                for (int t = wq; t < ntile; t += 2 * NW) {
+                    int pA, qA, pB, qB;
+                    df2_tri(t, pA, qA);
+                    const bool hasB = t + NW < ntile;
+                    df2_tri(hasB ? t + NW : t, pB, qB);
+                    df2_tile2(Cs, Up, Wn, t1 + 1 + pA, t1 + 1 + qA, t1 + 1 + pB, t1 + 1 + qB, hasB, g, t4);
+                }
+            }
+            __syncthreads();
+        } else {
+            const int ntile = nrem * (nrem + 1) / 2;
+            for (int t = warp; t < ntile; t += 2 * DF2_WARPS) {
+                int pA, qA, pB, qB;
+                df2_tri(t, pA, qA);
+                const bool hasB = t + DF2_WARPS < ntile;
+                df2_tri(hasB ? t + DF2_WARPS : t, pB, qB);
+                df2_tile2(Cs, Up, Wn, t1 + pA, t1 + qA, t1 + pB, t1 + qB, hasB, g, t4);
+            }
+            __syncthreads();
+            if (warp < DF2_PANEL_WARPS) {
+                const int j0 = t1 * NBD;
+                df2_panel(Cs, Upan + (t1 & 1) * NBD * LDP2, Wpan + (t1 & 1) * NBD * LDP2, dd, rdd, sgn, pc.c0, c.info, j0, min(NBD, w - j0),
+                          nt8 - j0, tid);
+            }
+            __syncthreads();
+        }
+    }
+    // l_jj = sqrt(|d_j|), l_ij = u_ij / (s_j l_jj)
+    if (tid < w) {
+        const double sk = sgn[tid];
+        const double l = sqrt(dd[tid] * sk);
+        dd[tid] = l;
+        rdd[tid] = 1.0 / (sk * l);
+    }
+    __syncthreads();
+    for (int k = q3; k < w; k += 3)
+        if (il < w && il >= k) D[(int64_t)k * ld + il] = (il == k) ? dd[k] : Cs[k * LDC2 + il] * rdd[k];
+    if (tid == 0) trace_mark(c, pc.level, 0, true);
+}
+
+// ------------------------------------------------------------------------------------------
 // k_trsm: 128 rows per CTA, 8 warps.  Columns are solved in blocks of 16: the contribution of the
 // already solved columns is a DMMA product (X[:, 0:j0] * (S L11[jb, 0:j0])'), the 16x16 diagonal
 // block is a register substitution (one row per thread).
@@ -309,6 +511,127 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_trsm(DevCtx c, int32_t begin)
         __syncthreads();
     }
     if (tid == 0) trace_mark(c, pc.level, 1, true);
+}
+
+// ------------------------------------------------------------------------------------------
+// k_trsm2 (round 2): the same solve with every global load issued once, up front: -S L11' (k-major) and the 64 x w block of
+// rows both sit in shared memory, so the eight 16-column steps run without a DRAM / L2 round trip each (k_trsm: the block
+// of L11, the diagonal block and the accumulators were fetched from global memory inside every step).  64 rows per CTA, two
+// CTAs per 128-row panel task; the DMMA products use two accumulator sets (even / odd k-steps) to halve the dependent chain.
+// ------------------------------------------------------------------------------------------
+constexpr int TR2_THREADS = 256;
+constexpr int TR2_ROWS = 64;
+constexpr int LDB2 = PIECE + 4;      // 132
+constexpr int LDX2 = TR2_ROWS + 4;   // 68
+
+__global__ void __launch_bounds__(TR2_THREADS, 1) k_trsm2(DevCtx c, int32_t begin) {
+    extern __shared__ double smem_d[];
+    double* Bs = smem_d;                       // [PIECE][LDB2]  Bs[k][n] = -L11[n, k] s_k  (n > k)
+    double* Xs = Bs + PIECE * LDB2;            // [PIECE][LDX2]  Xs[k][r]: rows of the panel, solved in place
+    double* invd = Xs + PIECE * LDX2;          // [PIECE]        1 / (s_k L11[k, k])
+    const PanelTask T = c.panel[begin + (blockIdx.x >> 1)];
+    const int half = blockIdx.x & 1;
+    const int32_t nr = min(TR2_ROWS, T.nr - half * TR2_ROWS);
+    if (nr <= 0) return;
+    const int32_t r0 = T.r0 + half * TR2_ROWS;
+    const Piece pc = c.pieces[T.piece];
+    const int32_t s = pc.sn;
+    if (c.skip && c.skip[s]) return;
+    const int32_t f = c.sn_first[s];
+    const int32_t ld = (int32_t)(c.sn_rowptr[s + 1] - c.sn_rowptr[s]);
+    const int32_t kb = pc.c0 - f, w = pc.c1 - pc.c0;
+    double* X = c.Lx + c.sn_xptr[s];
+    const double* L11 = X + (int64_t)kb * ld + kb;
+    const int8_t* sgn = c.sign + pc.c0;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t4 = lane & 3;
+    if (tid == 0 && half == 0) trace_mark(c, pc.level, 1, false);
+    const int nblk = (w + TRB - 1) / TRB, w16 = nblk * TRB;
+
+    {   // L11 (strictly lower part, negated, column signs applied) and the reciprocal diagonal
+        const int n = tid & (PIECE - 1), kq = tid >> 7;
+        for (int k0 = 0; k0 < w16; k0 += 16) {
+            double v[8];
+#pragma unroll
+            for (int x = 0; x < 8; ++x) {
+                const int k = k0 + kq + 2 * x;
+                v[x] = (k < w && n < w && n >= k) ? L11[(int64_t)k * ld + n] : 0.0;
+            }
+#pragma unroll
+            for (int x = 0; x < 8; ++x) {
+                const int k = k0 + kq + 2 * x;
+                const double sk = (k < w) ? (double)sgn[k] : 1.0;
+                if (n == k) invd[k] = (k < w) ? 1.0 / (sk * v[x]) : 1.0;
+                Bs[k * LDB2 + n] = (n > k) ? -v[x] * sk : 0.0;
+            }
+        }
+        // the rows of this CTA: Xs[k][r] = A21[r0 + r, k]
+        const int r = tid & (TR2_ROWS - 1), kq4 = tid >> 6;
+        for (int k0 = 0; k0 < w16; k0 += 32) {
+            double v[8];
+#pragma unroll
+            for (int x = 0; x < 8; ++x) {
+                const int k = k0 + kq4 + 4 * x;
+                v[x] = (k < w && r < nr) ? X[(int64_t)(kb + k) * ld + r0 + r] : 0.0;
+            }
+#pragma unroll
+            for (int x = 0; x < 8; ++x) {
+                const int k = k0 + kq4 + 4 * x;
+                if (k < w16) Xs[k * LDX2 + r] = v[x];
+            }
+        }
+    }
+    __syncthreads();
+
+    for (int b = 0; b < nblk; ++b) {
+        const int j0 = b * TRB;
+        if (j0 > 0) {
+            // Xs[j0 .. j0+15][rows of this warp] += Xs[0 .. j0) * Bs[0 .. j0)[j0 .. j0+15]
+            double acc[2][2], acc2[2][2];
+            const int rr = warp * 8 + g;
+#pragma unroll
+            for (int nj = 0; nj < 2; ++nj)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    acc[nj][e] = Xs[(j0 + nj * 8 + t4 * 2 + e) * LDX2 + rr];
+                    acc2[nj][e] = 0.0;
+                }
+            int k4 = 0;
+            for (; k4 + 8 <= j0; k4 += 8) {
+                const double a0 = Xs[(k4 + t4) * LDX2 + rr], a1 = Xs[(k4 + 4 + t4) * LDX2 + rr];
+                const double b00 = Bs[(k4 + t4) * LDB2 + j0 + g], b01 = Bs[(k4 + t4) * LDB2 + j0 + 8 + g];
+                const double b10 = Bs[(k4 + 4 + t4) * LDB2 + j0 + g], b11 = Bs[(k4 + 4 + t4) * LDB2 + j0 + 8 + g];
+                dmma884(acc[0][0], acc[0][1], a0, b00);
+                dmma884(acc[1][0], acc[1][1], a0, b01);
+                dmma884(acc2[0][0], acc2[0][1], a1, b10);
+                dmma884(acc2[1][0], acc2[1][1], a1, b11);
+            }
+#pragma unroll
+            for (int nj = 0; nj < 2; ++nj)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) Xs[(j0 + nj * 8 + t4 * 2 + e) * LDX2 + rr] = acc[nj][e] + acc2[nj][e];
+            __syncthreads();
+        }
+        if (tid < TR2_ROWS) {
+            // 16 x 16 diagonal block by substitution, one row per thread (right-looking: chain of 16 multiply-adds)
+            double t[TRB];
+#pragma unroll
+            for (int j = 0; j < TRB; ++j) t[j] = Xs[(j0 + j) * LDX2 + tid];
+#pragma unroll
+            for (int k = 0; k < TRB; ++k) {
+                t[k] *= invd[j0 + k];
+#pragma unroll
+                for (int j = k + 1; j < TRB; ++j) t[j] += t[k] * Bs[(j0 + k) * LDB2 + j0 + j];
+            }
+            const bool valid = tid < nr;
+#pragma unroll
+            for (int j = 0; j < TRB; ++j) {
+                Xs[(j0 + j) * LDX2 + tid] = t[j];
+                if (valid && j0 + j < w) X[(int64_t)(kb + j0 + j) * ld + r0 + tid] = t[j];
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0 && half == 0) trace_mark(c, pc.level, 1, true);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -471,8 +794,26 @@ __global__ void __launch_bounds__(UPD_THREADS, 4) k_update_lazy(DevCtx c, int32_
 static constexpr size_t DF_SMEM = ((size_t)PIECE * LDD + 3 * PIECE + (size_t)NBD * LDW + (size_t)PIECE * LDW) * 8;
 static constexpr size_t TR_SMEM = ((size_t)PIECE * LDX + (size_t)PIECE * LDLB + (size_t)TRB * LDX + (size_t)TRB * LDLD + TRB) * 8;
 
+static constexpr size_t DF2_SMEM = ((size_t)PIECE * LDC2 + 4 * (size_t)NBD * LDP2 + 3 * PIECE) * 8;
+static constexpr size_t TR2_SMEM = ((size_t)PIECE * LDB2 + (size_t)PIECE * LDX2 + PIECE) * 8;
+
+// TLPB200_CHAIN_KERNELS: 0 = round-1 k_diag_factor / k_trsm, 1 = k_diag_factor2 without look-ahead + k_trsm2, 2 (default) = with look-ahead
+static int chain_variant() {
+    static const int v = [] {
+        const char* e = getenv("TLPB200_CHAIN_KERNELS");
+        return e ? atoi(e) : 2;
+    }();
+    return v;
+}
+
 cudaError_t factor_kernels_static_init() {
     cudaError_t e;
+    e = cudaFuncSetAttribute(k_diag_factor2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DF2_SMEM);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_diag_factor2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DF2_SMEM);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_trsm2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TR2_SMEM);
+    if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_diag_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DF_SMEM);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TR_SMEM);
@@ -484,10 +825,16 @@ cudaError_t factor_kernels_static_init() {
 }
 
 void launch_diag_factor(const DevCtx& c, int32_t begin, int32_t end, cudaStream_t st) {
-    if (end > begin) k_diag_factor<<<end - begin, DF_THREADS, DF_SMEM, st>>>(c, begin);
+    if (end <= begin) return;
+    const int v = chain_variant();
+    if (v >= 2) k_diag_factor2<true><<<end - begin, DF2_THREADS, DF2_SMEM, st>>>(c, begin);
+    else if (v == 1) k_diag_factor2<false><<<end - begin, DF2_THREADS, DF2_SMEM, st>>>(c, begin);
+    else k_diag_factor<<<end - begin, DF_THREADS, DF_SMEM, st>>>(c, begin);
 }
 void launch_trsm(const DevCtx& c, int32_t begin, int32_t end, cudaStream_t st) {
-    if (end > begin) k_trsm<<<end - begin, TR_THREADS, TR_SMEM, st>>>(c, begin);
+    if (end <= begin) return;
+    if (chain_variant() >= 1) k_trsm2<<<2 * (end - begin), TR2_THREADS, TR2_SMEM, st>>>(c, begin);
+    else k_trsm<<<end - begin, TR_THREADS, TR_SMEM, st>>>(c, begin);
 }
 void launch_update(const DevCtx& c, int32_t begin, int32_t end, int atomic, cudaStream_t st) {
     if (end > begin) k_update<<<end - begin, UPD_THREADS, UPD_SMEM, st>>>(c, begin, atomic);
