@@ -15,10 +15,34 @@
 
 namespace tlp {
 
+// scripts/chain_bench.cu compiles this file with TLP_CHAIN_CLOCKS to read the phase timeline of one CTA
+#ifdef TLP_CHAIN_CLOCKS
+__device__ unsigned long long g_ticks[2][80];
+#define TLP_TICK(idx)                                                            \
+    do {                                                                         \
+        if (blockIdx.x == 0 && threadIdx.x == 0) g_ticks[0][idx] = clock64();    \
+        if (blockIdx.x == 0 && threadIdx.x == 128) g_ticks[1][idx] = clock64();  \
+    } while (0)
+#else
+#define TLP_TICK(idx)
+#endif
+
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));
+}
+// FP64 operations whose relative order the compiler keeps (volatile): the chain kernels below are bound by the latency of
+// dependent DFMAs (~18 cycles), so the order in which independent ones are issued between them is the schedule.
+__device__ __forceinline__ double vfma(double a, double b, double c) {
+    double d;
+    asm volatile("fma.rn.f64 %0, %1, %2, %3;" : "=d"(d) : "d"(a), "d"(b), "d"(c));
+    return d;
+}
+__device__ __forceinline__ double vmul(double a, double b) {
+    double d;
+    asm volatile("mul.rn.f64 %0, %1, %2;" : "=d"(d) : "d"(a), "d"(b));
+    return d;
 }
 __device__ __forceinline__ void cp_async8_zfill(void* smem, const void* gmem, bool valid) {
     const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
@@ -106,6 +130,7 @@ __global__ void __launch_bounds__(DF_THREADS, 1) k_diag_factor(DevCtx c, int32_t
     const int il = tid & (PIECE - 1), q4 = tid >> 7;
 
     if (tid == 0) trace_mark(c, pc.level, 0, false);
+    TLP_TICK(0);
     if (tid < w) sgn[tid] = (double)c.sign[pc.c0 + tid];
     for (int kb = 0; kb < w; kb += 32) {       // 8 independent loads in flight per thread
         double v[8];
@@ -213,110 +238,139 @@ __global__ void __launch_bounds__(DF_THREADS, 1) k_diag_factor(DevCtx c, int32_t
     __syncthreads();
     for (int k = q4; k < w; k += 4)
         if (il < w && il >= k) D[(int64_t)k * ld + il] = (il == k) ? dd[k] : Cs[k * LDD + il] * rdd[k];
+    TLP_TICK(72);
     if (tid == 0) trace_mark(c, pc.level, 0, true);
 }
 
 // ------------------------------------------------------------------------------------------
-// k_diag_factor2 (round 2): same elimination (unscaled columns u_ij, signed pivots d_j, W = U D^-1) reorganised around the
-// two things that bound a 128-column block on one SM:
-//  * the pivot chain.  Every thread of the panel warps carries a private copy of the 8x8 diagonal block in registers and
-//    eliminates it redundantly next to its own row: no shuffle, no shared-memory hand-over and no block-wide barrier between
-//    the diagonal block and the rows below it -- per column the chain is one reciprocal and two FMAs.
-//  * the FP64 pipe.  The trailing update C -= U W' runs on DMMA 8x8x4 tiles straight out of shared memory (two k-steps per
-//    8-column block).  With look-ahead the tiles of the NEXT 8 columns are updated first by all warps; then warps 0-3
-//    eliminate that block while the other warps finish the rest of the trailing matrix underneath.
+// k_diag_factor2 (round 2): same elimination (unscaled columns u_ij, signed pivots d_j, W = U D^-1), rebuilt on what
+// scripts/chain_bench.cu measures on B200: a dependent DFMA costs 8 cycles but ONE warp also issues at most one FP64
+// instruction per 8 cycles (a DMMA per 16, 26 dependent), MUFU.RCP64H 19, a shuffle 26, a full 1.0/d 83, and one SM pulls
+// only ~16 B/clk out of L2 with 8-byte loads.  k_diag_factor (104 k cycles) is bound by barriers and FMA-issue; here
+//  * the panel (8 columns x all rows below) is done by five warps, each holding the eight diagonal rows in lanes 0-7 and 24
+//    other rows in lanes 8-31: pivots and the rows of the diagonal block travel by shuffle inside the warp, so there is no
+//    shared-memory hand-over and no block-wide barrier inside a panel, and a warp issues 68 FP64 instructions per panel (a
+//    private copy of the 8x8 block per thread, the previous layout, cost 220: 1 800 cycles of pure issue).  The reciprocal
+//    is the hardware seed plus one cubic step (3 FMAs, error e^3 < 2^-57), with the sign test beside it, off the chain.
+//  * the trailing update C -= U W' runs on DMMA 8x8x4 tiles straight out of shared memory, four tiles of a tile row in
+//    flight per warp.  The tiles of the NEXT 8 columns are updated first by all warps; then the panel warps eliminate that
+//    block while the other eleven finish the rest of the trailing matrix underneath.
+//  * block copy in / out with 16 independent loads / stores per thread in flight.
 // Layout: Cs column-major [128][130] (130: conflict-free accumulator fragments), U / -W panels [2][8][132] double-buffered.
 // ------------------------------------------------------------------------------------------
-constexpr int DF2_THREADS = 384;
+constexpr int DF2_THREADS = 512;
 constexpr int DF2_WARPS = DF2_THREADS / 32;
-constexpr int DF2_PANEL_WARPS = 4;
+constexpr int DF2_PANEL_WARPS = 5;                       // 8 diagonal rows (replicated) + 24 rows per warp: 5 x 24 = 120 rows below
+constexpr int DF2_TRAIL_WARPS = DF2_WARPS - DF2_PANEL_WARPS;
 constexpr int LDC2 = PIECE + 2;
 constexpr int LDP2 = PIECE + 4;
 
-// rows j0 + t (t = thread index inside the panel warps) of the 8 columns j0 .. j0+7
+// 1 / d to within an ulp or two: the 20-bit hardware seed and one cubic step r0 (1 + e + e^2), e = 1 - d r0  (error e^3)
+__device__ __forceinline__ double fast_rcp(double d) {
+    double r0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(d));
+    const double e = fma(-d, r0, 1.0);
+    const double p = fma(e, e, e);
+    return fma(r0, p, r0);
+}
+
+// columns j0 .. j0+7, all rows from j0 down (nrows of them); called by the DF2_PANEL_WARPS panel warps
 __device__ __forceinline__ void df2_panel(double* Cs, double* Up, double* Wn, double* dd, double* rdd, const double* sgn,
-                                          int32_t gcol0, int32_t* info, int j0, int nb, int nrows, int t) {
+                                          int32_t gcol0, int32_t* info, int j0, int nb, int nrows, int wp, int lane) {
+    const int t = (lane < NBD) ? lane : NBD + 24 * wp + (lane - NBD);      // row offset inside the panel
     const bool live = t < nrows;
     const int i = j0 + (live ? t : 0);
-    double g[NBD][NBD];     // private copy of the diagonal block (lower part)
-    double u[NBD], rr[NBD];
+    double u[NBD], an[NBD], sg[NBD];
 #pragma unroll
     for (int j = 0; j < NBD; ++j) {
-#pragma unroll
-        for (int k = j; k < NBD; ++k) g[k][j] = Cs[(j0 + j) * LDC2 + j0 + k];
         u[j] = Cs[(j0 + j) * LDC2 + i];
+        sg[j] = sgn[j0 + j];
     }
-    // the threads of the diagonal rows write their eliminated entries back over the block every other thread has just read
+    // warp 0 writes the eliminated diagonal rows back over the block the other panel warps have just read
     asm volatile("bar.sync 1, %0;" ::"n"(DF2_PANEL_WARPS * 32) : "memory");
-    if (!live) return;
+    unsigned bad = 0;
+    double dmine = 1.0, rmine = 1.0;
 #pragma unroll
     for (int j = 0; j < NBD; ++j) {
-        double d = g[j][j];
-        const double sj = sgn[j0 + j];
-        if (!(d * sj > 0.0)) {
-            if (t == j && j < nb) atomicMin(info, gcol0 + j0 + j);
-            d = sj;
+        const double draw = __shfl_sync(0xffffffffu, u[j], j);      // pivot: lane j holds diagonal row j
+        const bool ok = draw * sg[j] > 0.0;                           // beside the seed, not in front of it
+        double r0;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(draw));
+        r0 = ok ? r0 : sg[j];                                         // failed sign test: pivot replaced by s_j, as in k_diag_factor
+        const double d = ok ? draw : sg[j];
+        if (!ok) bad |= 1u << j;
+        const double e = fma(-d, r0, 1.0);
+        const double pe = fma(e, e, e);
+        const double r = fma(r0, pe, r0);
+        if (lane == j) { dmine = d; rmine = r; }
+        const double a = u[j] * r;
+        an[j] = a;
+#pragma unroll
+        for (int k = j + 1; k < NBD; ++k) {
+            const double ukj = __shfl_sync(0xffffffffu, u[j], k);     // u_kj from diagonal row k
+            u[k] = fma(-a, ukj, u[k]);
         }
-        const double r = 1.0 / d;
-        rr[j] = r;
-        if (t == j) { dd[j0 + j] = d; rdd[j0 + j] = r; }
-        double m[NBD];
-#pragma unroll
-        for (int l = j + 1; l < NBD; ++l) m[l] = g[l][j] * r;
-#pragma unroll
-        for (int k = j + 1; k < NBD; ++k)
-#pragma unroll
-            for (int l = j + 1; l <= k; ++l) g[k][l] -= g[k][j] * m[l];
-        const double a = u[j];
-#pragma unroll
-        for (int l = j + 1; l < NBD; ++l) u[l] -= a * m[l];
     }
-    if (t < NBD) {
+    if (!live) return;
+    if (lane < NBD) {
+        if (wp == 0) {
 #pragma unroll
-        for (int j = 0; j < NBD; ++j)
-            if (j <= t) Cs[(j0 + j) * LDC2 + i] = u[j];
+            for (int j = 0; j < NBD; ++j)
+                if (j < lane) Cs[(j0 + j) * LDC2 + i] = u[j];
+            Cs[(j0 + lane) * LDC2 + i] = dmine;      // the pivot actually used
+            dd[j0 + lane] = dmine;
+            rdd[j0 + lane] = rmine;
+            if (((bad >> lane) & 1u) && lane < nb) atomicMin(info, gcol0 + j0 + lane);
+        }
     } else {
 #pragma unroll
         for (int j = 0; j < NBD; ++j) {
             Cs[(j0 + j) * LDC2 + i] = u[j];
             Up[j * LDP2 + i] = u[j];
-            Wn[j * LDP2 + i] = -u[j] * rr[j];
+            Wn[j * LDP2 + i] = -an[j];
         }
     }
 }
 
-// C[8ti.., 8tk..] += U[8ti.., :] * Wn[8tk.., :]'   (one 8x8 tile, K = 8)
-__device__ __forceinline__ void df2_tile2(double* Cs, const double* Up, const double* Wn, int tiA, int tkA, int tiB, int tkB, bool hasB,
-                                          int g, int t4) {
-    const double a0 = Up[t4 * LDP2 + 8 * tiA + g], a1 = Up[(4 + t4) * LDP2 + 8 * tiA + g];
-    const double b0 = Wn[t4 * LDP2 + 8 * tkA + g], b1 = Wn[(4 + t4) * LDP2 + 8 * tkA + g];
-    const double e0 = Up[t4 * LDP2 + 8 * tiB + g], e1 = Up[(4 + t4) * LDP2 + 8 * tiB + g];
-    const double f0 = Wn[t4 * LDP2 + 8 * tkB + g], f1 = Wn[(4 + t4) * LDP2 + 8 * tkB + g];
-    double* pa = Cs + (8 * tkA + 2 * t4) * LDC2 + 8 * tiA + g;
-    double* pb = Cs + (8 * tkB + 2 * t4) * LDC2 + 8 * tiB + g;
-    double c0 = pa[0], c1 = pa[LDC2];
-    double h0 = pb[0], h1 = pb[LDC2];
-    dmma884(c0, c1, a0, b0);
-    dmma884(h0, h1, e0, f0);
-    dmma884(c0, c1, a1, b1);
-    dmma884(h0, h1, e1, f1);
-    pa[0] = c0;
-    pa[LDC2] = c1;
-    if (hasB) {
-        pb[0] = h0;
-        pb[LDC2] = h1;
+// n <= 4 tiles (ti, tk0 .. tk0+n-1) of one tile row: C[8ti.., 8tk..] += U[8ti.., 0:8] * Wn[8tk.., 0:8]'.  The second k-step of a
+// tile issues four DMMAs (64 cycles) after its first: no wait on the 26-cycle accumulate latency.
+__device__ __forceinline__ void df2_quad(double* Cs, const double* Up, const double* Wn, int ti, int tk0, int n, int g, int t4) {
+    const double a0 = Up[t4 * LDP2 + 8 * ti + g], a1 = Up[(4 + t4) * LDP2 + 8 * ti + g];
+    double b0[4], b1[4], c0[4], c1[4];
+    double* pc[4];
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+        const int tk = tk0 + min(x, n - 1);      // past the end: the last tile again, result dropped
+        b0[x] = Wn[t4 * LDP2 + 8 * tk + g];
+        b1[x] = Wn[(4 + t4) * LDP2 + 8 * tk + g];
+        pc[x] = Cs + (8 * tk + 2 * t4) * LDC2 + 8 * ti + g;
+        c0[x] = pc[x][0];
+        c1[x] = pc[x][LDC2];
     }
+#pragma unroll
+    for (int x = 0; x < 4; ++x) dmma884(c0[x], c1[x], a0, b0[x]);
+#pragma unroll
+    for (int x = 0; x < 4; ++x) dmma884(c0[x], c1[x], a1, b1[x]);
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+        if (x < n) {
+            pc[x][0] = c0[x];
+            pc[x][LDC2] = c1[x];
+        }
 }
 
-// t-th tile (row-major over the lower triangle p >= q >= 0)
-__device__ __forceinline__ void df2_tri(int t, int& p, int& q) {
-    p = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
-    while (p * (p + 1) / 2 > t) --p;
-    while ((p + 1) * (p + 2) / 2 <= t) ++p;
-    q = t - p * (p + 1) / 2;
+// one tile: the strip of the next block (two dependent DMMAs)
+__device__ __forceinline__ void df2_tile1(double* Cs, const double* Up, const double* Wn, int ti, int tk, int g, int t4) {
+    const double a0 = Up[t4 * LDP2 + 8 * ti + g], a1 = Up[(4 + t4) * LDP2 + 8 * ti + g];
+    const double b0 = Wn[t4 * LDP2 + 8 * tk + g], b1 = Wn[(4 + t4) * LDP2 + 8 * tk + g];
+    double* pc = Cs + (8 * tk + 2 * t4) * LDC2 + 8 * ti + g;
+    double c0 = pc[0], c1 = pc[LDC2];
+    dmma884(c0, c1, a0, b0);
+    dmma884(c0, c1, a1, b1);
+    pc[0] = c0;
+    pc[LDC2] = c1;
 }
 
-template <bool LOOKAHEAD>
 __global__ void __launch_bounds__(DF2_THREADS, 1) k_diag_factor2(DevCtx c, int32_t begin) {
     extern __shared__ double smem_d[];
     double* Cs = smem_d;                       // [PIECE][LDC2] column-major
@@ -334,76 +388,68 @@ __global__ void __launch_bounds__(DF2_THREADS, 1) k_diag_factor2(DevCtx c, int32
     double* D = c.Lx + c.sn_xptr[s] + (int64_t)lc0 * ld + lc0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t4 = lane & 3;
-    const int il = tid & (PIECE - 1), q3 = tid >> 7;      // 3 columns per pass of the block copy
+    const int il = tid & (PIECE - 1), q4 = tid >> 7;      // 4 columns per pass of the block copy
     const int nt = (w + NBD - 1) / NBD, nt8 = nt * NBD;
 
     if (tid == 0) trace_mark(c, pc.level, 0, false);
+    TLP_TICK(0);
+    // lower triangle in, 16 loads in flight per thread; zero elsewhere in the nt8 x 128 window except above the diagonal
+    // tiles, which nothing reads
     if (tid < PIECE) sgn[tid] = (tid < w) ? (double)c.sign[pc.c0 + tid] : 1.0;
-    // lower triangle in, everything else of the nt8 x 128 window zero, unit diagonal on the padding columns
-    for (int kb = 0; kb < nt8; kb += 24) {
-        double v[8];
+    for (int kb = 0; kb < nt8; kb += 64) {
+        double v[16];
 #pragma unroll
-        for (int x = 0; x < 8; ++x) {
-            const int k = kb + q3 + 3 * x;
-            v[x] = (k < w && il < w && il >= k) ? D[(int64_t)k * ld + il] : ((k == il && k >= w) ? 1.0 : 0.0);
+        for (int x = 0; x < 16; ++x) {
+            const int k = kb + q4 + 4 * x;
+            v[x] = (k < w && il < w && il >= k) ? D[(int64_t)k * ld + il] : 0.0;
         }
 #pragma unroll
-        for (int x = 0; x < 8; ++x) {
-            const int k = kb + q3 + 3 * x;
-            if (k < nt8) Cs[k * LDC2 + il] = v[x];
+        for (int x = 0; x < 16; ++x) {
+            const int k = kb + q4 + 4 * x;
+            if (k < nt8 && (il | 31) >= (k & ~7)) Cs[k * LDC2 + il] = v[x];
         }
     }
     __syncthreads();
-    if (warp < DF2_PANEL_WARPS) df2_panel(Cs, Upan, Wpan, dd, rdd, sgn, pc.c0, c.info, 0, min(NBD, w), nt8, tid);
+    if (tid >= w && tid < nt8) Cs[tid * LDC2 + tid] = 1.0;      // unit diagonal on the padding columns
+    __syncthreads();
+    TLP_TICK(1);
+    if (warp < DF2_PANEL_WARPS) df2_panel(Cs, Upan, Wpan, dd, rdd, sgn, pc.c0, c.info, 0, min(NBD, w), nt8, warp, lane);
+    TLP_TICK(2);
     __syncthreads();
     for (int b = 0; b + 1 < nt; ++b) {
         const double* Up = Upan + (b & 1) * NBD * LDP2;
         const double* Wn = Wpan + (b & 1) * NBD * LDP2;
         const int t1 = b + 1;               // first trailing tile row / column
-        const int nrem = nt - t1;           // tile rows left
-        if (LOOKAHEAD) {
-            // (1) columns of the next block, all warps: tiles (t1 + x, t1)
-            for (int x = warp; x < nrem; x += 2 * DF2_WARPS) {
-                const bool hasB = x + DF2_WARPS < nrem;
-                df2_tile2(Cs, Up, Wn, t1 + x, t1, hasB ? t1 + x + DF2_WARPS : t1 + x, t1, hasB, g, t4);
-            }
-            __syncthreads();
-            // (2) panel warps eliminate the next block; the others finish the trailing matrix (tile columns >= t1 + 1)
-            if (warp < DF2_PANEL_WARPS) {
-                const int j0 = t1 * NBD;
-                df2_panel(Cs, Upan + (t1 & 1) * NBD * LDP2, Wpan + (t1 & 1) * NBD * LDP2, dd, rdd, sgn, pc.c0, c.info, j0, min(NBD, w - j0),
-                          nt8 - j0, tid);
-            } else {
-                constexpr int NW = DF2_WARPS - DF2_PANEL_WARPS;
-                const int T = nrem - 1, ntile = T * (T + 1) / 2, wq = warp - DF2_PANEL_WARPS;
-                for (int t = wq; t < ntile; t += 2 * NW) {
-                    int pA, qA, pB, qB;
-                    df2_tri(t, pA, qA);
-                    const bool hasB = t + NW < ntile;
-                    df2_tri(hasB ? t + NW : t, pB, qB);
-                    df2_tile2(Cs, Up, Wn, t1 + 1 + pA, t1 + 1 + qA, t1 + 1 + pB, t1 + 1 + qB, hasB, g, t4);
-                }
-            }
-            __syncthreads();
+        const int nrem = nt - t1;           // tile rows left (<= 15)
+        // (1) columns of the next block: tiles (t1 + x, t1), one per warp
+        if (warp < nrem) df2_tile1(Cs, Up, Wn, t1 + warp, t1, g, t4);
+        TLP_TICK(3 + 4 * b);
+        __syncthreads();
+        TLP_TICK(4 + 4 * b);
+        // (2) panel warps eliminate the next block; the others finish the trailing matrix (tile columns >= t1 + 1)
+        if (warp < DF2_PANEL_WARPS) {
+            const int j0 = t1 * NBD;
+            df2_panel(Cs, Upan + (t1 & 1) * NBD * LDP2, Wpan + (t1 & 1) * NBD * LDP2, dd, rdd, sgn, pc.c0, c.info, j0, min(NBD, w - j0), nt8 - j0,
+                      warp, lane);
         } else {
-            const int ntile = nrem * (nrem + 1) / 2;
-            for (int t = warp; t < ntile; t += 2 * DF2_WARPS) {
-                int pA, qA, pB, qB;
-                df2_tri(t, pA, qA);
-                const bool hasB = t + DF2_WARPS < ntile;
-                df2_tri(hasB ? t + DF2_WARPS : t, pB, qB);
-                df2_tile2(Cs, Up, Wn, t1 + pA, t1 + qA, t1 + pB, t1 + qB, hasB, g, t4);
+            // trailing tile rows p = 0 .. T-1 (row p: tiles q = 0 .. p), cut into quads (p, 4qq .. 4qq+3), p >= 4qq, listed column
+            // quad by column quad; quad number idx -> warp idx mod DF2_TRAIL_WARPS
+            const int T = nrem - 1, c0t = t1 + 1;
+            int nq = 0;
+            for (int qq = 0; 4 * qq < T; ++qq) nq += T - 4 * qq;
+            for (int idx = warp - DF2_PANEL_WARPS; idx < nq; idx += DF2_TRAIL_WARPS) {
+                int rem = idx, qq = 0;
+                while (rem >= T - 4 * qq) { rem -= T - 4 * qq; ++qq; }
+                const int p = 4 * qq + rem;
+                df2_quad(Cs, Up, Wn, c0t + p, c0t + 4 * qq, min(4, p + 1 - 4 * qq), g, t4);
             }
-            __syncthreads();
-            if (warp < DF2_PANEL_WARPS) {
-                const int j0 = t1 * NBD;
-                df2_panel(Cs, Upan + (t1 & 1) * NBD * LDP2, Wpan + (t1 & 1) * NBD * LDP2, dd, rdd, sgn, pc.c0, c.info, j0, min(NBD, w - j0),
-                          nt8 - j0, tid);
-            }
-            __syncthreads();
         }
+        TLP_TICK(5 + 4 * b);
+        __syncthreads();
+        TLP_TICK(6 + 4 * b);
     }
     // l_jj = sqrt(|d_j|), l_ij = u_ij / (s_j l_jj)
+    TLP_TICK(70);
     if (tid < w) {
         const double sk = sgn[tid];
         const double l = sqrt(dd[tid] * sk);
@@ -411,8 +457,21 @@ __global__ void __launch_bounds__(DF2_THREADS, 1) k_diag_factor2(DevCtx c, int32
         rdd[tid] = 1.0 / (sk * l);
     }
     __syncthreads();
-    for (int k = q3; k < w; k += 3)
-        if (il < w && il >= k) D[(int64_t)k * ld + il] = (il == k) ? dd[k] : Cs[k * LDC2 + il] * rdd[k];
+    TLP_TICK(71);
+    for (int kb = 0; kb < w; kb += 64) {
+        double v[16];
+#pragma unroll
+        for (int x = 0; x < 16; ++x) {
+            const int k = kb + q4 + 4 * x;
+            v[x] = (k < w && il < w && il >= k) ? ((il == k) ? dd[k] : Cs[k * LDC2 + il] * rdd[k]) : 0.0;
+        }
+#pragma unroll
+        for (int x = 0; x < 16; ++x) {
+            const int k = kb + q4 + 4 * x;
+            if (k < w && il < w && il >= k) D[(int64_t)k * ld + il] = v[x];
+        }
+    }
+    TLP_TICK(72);
     if (tid == 0) trace_mark(c, pc.level, 0, true);
 }
 
@@ -447,6 +506,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_trsm(DevCtx c, int32_t begin)
     const int8_t* sgn = c.sign + pc.c0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t4 = lane & 3;
     if (tid == 0) trace_mark(c, pc.level, 1, false);
+    TLP_TICK(0);
     const int nblk = (w + TRB - 1) / TRB;
 
     for (int b = 0; b < nblk; ++b) {
@@ -510,25 +570,32 @@ __global__ void __launch_bounds__(TR_THREADS, 1) k_trsm(DevCtx c, int32_t begin)
         }
         __syncthreads();
     }
+    TLP_TICK(20);
     if (tid == 0) trace_mark(c, pc.level, 1, true);
 }
 
 // ------------------------------------------------------------------------------------------
-// k_trsm2 (round 2): the same solve with every global load issued once, up front: -S L11' (k-major) and the 64 x w block of
-// rows both sit in shared memory, so the eight 16-column steps run without a DRAM / L2 round trip each (k_trsm: the block
-// of L11, the diagonal block and the accumulators were fetched from global memory inside every step).  64 rows per CTA, two
-// CTAs per 128-row panel task; the DMMA products use two accumulator sets (even / odd k-steps) to halve the dependent chain.
+// k_trsm2 (round 2): the same solve with every global load issued once, up front, as asynchronous copies: L11 (k-major, as
+// stored) and the 64 x w block of rows both sit in shared memory, so the eight 16-column steps run without an L2 round trip
+// each (k_trsm fetched its block of L11, the diagonal block and the accumulators from global memory inside every step;
+// scripts/chain_bench.cu: 50.8 k cycles per CTA).  64 rows per CTA, two CTAs per 128-row panel task.  Solved columns are
+// kept in shared memory as -s_k x_k, so the products X[:, 0:j0] S L11[j0:j0+16, 0:j0]' need no operand fix-up and use two
+// accumulator sets (even / odd k-steps: a dependent DMMA costs ~100 cycles).  The 16 x 16 diagonal blocks are pre-scaled
+// (c_jk = L_jk s_k / (s_k L_kk)) so that the substitution chain is one FMA per column instead of a multiply and an FMA.
 // ------------------------------------------------------------------------------------------
 constexpr int TR2_THREADS = 256;
 constexpr int TR2_ROWS = 64;
 constexpr int LDB2 = PIECE + 4;      // 132
 constexpr int LDX2 = TR2_ROWS + 4;   // 68
+constexpr int LDCD = TRB + 1;        // 17
 
 __global__ void __launch_bounds__(TR2_THREADS, 1) k_trsm2(DevCtx c, int32_t begin) {
     extern __shared__ double smem_d[];
-    double* Bs = smem_d;                       // [PIECE][LDB2]  Bs[k][n] = -L11[n, k] s_k  (n > k)
-    double* Xs = Bs + PIECE * LDB2;            // [PIECE][LDX2]  Xs[k][r]: rows of the panel, solved in place
-    double* invd = Xs + PIECE * LDX2;          // [PIECE]        1 / (s_k L11[k, k])
+    double* Bs = smem_d;                       // [PIECE][LDB2]  Bs[k][n] = L11[n, k]  (n >= k, else 0)
+    double* Xs = Bs + PIECE * LDB2;            // [PIECE][LDX2]  Xs[k][r]: rows of the panel; solved columns as -s_k x_k
+    double* Cd = Xs + PIECE * LDX2;            // [PIECE][LDCD]  Cd[k][j] = L11[j0 + j, k] / L11[k, k] inside k's 16-block (j0 + j > k)
+    double* invd = Cd + PIECE * LDCD;          // [PIECE]        1 / (s_k L11[k, k])
+    double* sgd = invd + PIECE;                // [PIECE]        s_k
     const PanelTask T = c.panel[begin + (blockIdx.x >> 1)];
     const int half = blockIdx.x & 1;
     const int32_t nr = min(TR2_ROWS, T.nr - half * TR2_ROWS);
@@ -542,94 +609,123 @@ __global__ void __launch_bounds__(TR2_THREADS, 1) k_trsm2(DevCtx c, int32_t begi
     const int32_t kb = pc.c0 - f, w = pc.c1 - pc.c0;
     double* X = c.Lx + c.sn_xptr[s];
     const double* L11 = X + (int64_t)kb * ld + kb;
-    const int8_t* sgn = c.sign + pc.c0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t4 = lane & 3;
     if (tid == 0 && half == 0) trace_mark(c, pc.level, 1, false);
-    const int nblk = (w + TRB - 1) / TRB, w16 = nblk * TRB;
+    TLP_TICK(0);
+    const int nblk = (w + TRB - 1) / TRB, w16 = nblk * TRB, ngrp = (w16 + 31) / 32;
 
-    {   // L11 (strictly lower part, negated, column signs applied) and the reciprocal diagonal
-        const int n = tid & (PIECE - 1), kq = tid >> 7;
-        for (int k0 = 0; k0 < w16; k0 += 16) {
-            double v[8];
+    // Operands arrive in groups of 32 columns; the loads of group g + 1 are in flight (in registers) while the two 16-column
+    // steps of group g run: one SM pulls only ~16 B/clk out of L2, all 130 KB up front cost 10 k cycles of the 38 k.
+    if (tid < PIECE) sgd[tid] = (tid < w) ? (double)c.sign[pc.c0 + tid] : 1.0;
+    const int n = tid & (PIECE - 1), kq = tid >> 7;          // L11: row n, columns 32 g + kq + 2 x
+    const int r = tid & (TR2_ROWS - 1), kq4 = tid >> 6;      // rows of the panel: row r, columns 32 g + kq4 + 4 x
+    double vb[16], vx[8];
+    auto issue = [&](int gidx) {
 #pragma unroll
-            for (int x = 0; x < 8; ++x) {
-                const int k = k0 + kq + 2 * x;
-                v[x] = (k < w && n < w && n >= k) ? L11[(int64_t)k * ld + n] : 0.0;
-            }
-#pragma unroll
-            for (int x = 0; x < 8; ++x) {
-                const int k = k0 + kq + 2 * x;
-                const double sk = (k < w) ? (double)sgn[k] : 1.0;
-                if (n == k) invd[k] = (k < w) ? 1.0 / (sk * v[x]) : 1.0;
-                Bs[k * LDB2 + n] = (n > k) ? -v[x] * sk : 0.0;
-            }
+        for (int x = 0; x < 16; ++x) {
+            const int k = 32 * gidx + kq + 2 * x;
+            vb[x] = (k < w && n < w && n >= k) ? L11[(int64_t)k * ld + n] : 0.0;
         }
-        // the rows of this CTA: Xs[k][r] = A21[r0 + r, k]
-        const int r = tid & (TR2_ROWS - 1), kq4 = tid >> 6;
-        for (int k0 = 0; k0 < w16; k0 += 32) {
-            double v[8];
 #pragma unroll
-            for (int x = 0; x < 8; ++x) {
-                const int k = k0 + kq4 + 4 * x;
-                v[x] = (k < w && r < nr) ? X[(int64_t)(kb + k) * ld + r0 + r] : 0.0;
-            }
-#pragma unroll
-            for (int x = 0; x < 8; ++x) {
-                const int k = k0 + kq4 + 4 * x;
-                if (k < w16) Xs[k * LDX2 + r] = v[x];
-            }
+        for (int x = 0; x < 8; ++x) {
+            const int k = 32 * gidx + kq4 + 4 * x;
+            vx[x] = (k < w && r < nr) ? X[(int64_t)(kb + k) * ld + r0 + r] : 0.0;
         }
-    }
+    };
+    auto commit = [&](int gidx) {
+#pragma unroll
+        for (int x = 0; x < 16; ++x) {
+            const int k = 32 * gidx + kq + 2 * x;
+            if (k < w16 && n >= 32 * gidx) Bs[k * LDB2 + n] = vb[x];      // rows above the group's diagonal blocks: never read
+        }
+#pragma unroll
+        for (int x = 0; x < 8; ++x) {
+            const int k = 32 * gidx + kq4 + 4 * x;
+            if (k < w16) Xs[k * LDX2 + r] = vx[x];
+        }
+    };
+    issue(0);
+    commit(0);
     __syncthreads();
+    TLP_TICK(1);
 
-    for (int b = 0; b < nblk; ++b) {
-        const int j0 = b * TRB;
-        if (j0 > 0) {
-            // Xs[j0 .. j0+15][rows of this warp] += Xs[0 .. j0) * Bs[0 .. j0)[j0 .. j0+15]
-            double acc[2][2], acc2[2][2];
-            const int rr = warp * 8 + g;
-#pragma unroll
-            for (int nj = 0; nj < 2; ++nj)
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    acc[nj][e] = Xs[(j0 + nj * 8 + t4 * 2 + e) * LDX2 + rr];
-                    acc2[nj][e] = 0.0;
-                }
-            int k4 = 0;
-            for (; k4 + 8 <= j0; k4 += 8) {
-                const double a0 = Xs[(k4 + t4) * LDX2 + rr], a1 = Xs[(k4 + 4 + t4) * LDX2 + rr];
-                const double b00 = Bs[(k4 + t4) * LDB2 + j0 + g], b01 = Bs[(k4 + t4) * LDB2 + j0 + 8 + g];
-                const double b10 = Bs[(k4 + 4 + t4) * LDB2 + j0 + g], b11 = Bs[(k4 + 4 + t4) * LDB2 + j0 + 8 + g];
-                dmma884(acc[0][0], acc[0][1], a0, b00);
-                dmma884(acc[1][0], acc[1][1], a0, b01);
-                dmma884(acc2[0][0], acc2[0][1], a1, b10);
-                dmma884(acc2[1][0], acc2[1][1], a1, b11);
-            }
-#pragma unroll
-            for (int nj = 0; nj < 2; ++nj)
-#pragma unroll
-                for (int e = 0; e < 2; ++e) Xs[(j0 + nj * 8 + t4 * 2 + e) * LDX2 + rr] = acc[nj][e] + acc2[nj][e];
-            __syncthreads();
-        }
-        if (tid < TR2_ROWS) {
-            // 16 x 16 diagonal block by substitution, one row per thread (right-looking: chain of 16 multiply-adds)
-            double t[TRB];
-#pragma unroll
-            for (int j = 0; j < TRB; ++j) t[j] = Xs[(j0 + j) * LDX2 + tid];
-#pragma unroll
-            for (int k = 0; k < TRB; ++k) {
-                t[k] *= invd[j0 + k];
-#pragma unroll
-                for (int j = k + 1; j < TRB; ++j) t[j] += t[k] * Bs[(j0 + k) * LDB2 + j0 + j];
-            }
-            const bool valid = tid < nr;
-#pragma unroll
-            for (int j = 0; j < TRB; ++j) {
-                Xs[(j0 + j) * LDX2 + tid] = t[j];
-                if (valid && j0 + j < w) X[(int64_t)(kb + j0 + j) * ld + r0 + tid] = t[j];
-            }
+    for (int gidx = 0; gidx < ngrp; ++gidx) {
+        if (gidx + 1 < ngrp) issue(gidx + 1);
+        if (tid < 32) {
+            const int k = 32 * gidx + tid;
+            if (k < w16) invd[k] = (k < w) ? 1.0 / (sgd[k] * Bs[k * LDB2 + k]) : 1.0;
         }
         __syncthreads();
+        for (int e = tid; e < 32 * TRB; e += TR2_THREADS) {
+            const int k = 32 * gidx + (e >> 4), j = e & 15, nn = (k & ~(TRB - 1)) + j;
+            if (k < w16) Cd[k * LDCD + j] = (nn > k) ? Bs[k * LDB2 + nn] * sgd[k] * invd[k] : 0.0;
+        }
+        __syncthreads();
+        for (int b = 2 * gidx; b < min(2 * gidx + 2, nblk); ++b) {
+            const int j0 = b * TRB;
+            if (j0 > 0) {
+                // Xs[j0 .. j0+15][rows of this warp] += (-X S)[:, 0 .. j0) * L11[j0 .. j0+15, 0 .. j0)'
+                double acc[2][2], acc2[2][2];
+                const int rr = warp * 8 + g;
+#pragma unroll
+                for (int nj = 0; nj < 2; ++nj)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        acc[nj][e] = Xs[(j0 + nj * 8 + t4 * 2 + e) * LDX2 + rr];
+                        acc2[nj][e] = 0.0;
+                    }
+#pragma unroll 2
+                for (int k4 = 0; k4 < j0; k4 += 8) {
+                    const double a0 = Xs[(k4 + t4) * LDX2 + rr], a1 = Xs[(k4 + 4 + t4) * LDX2 + rr];
+                    const double b00 = Bs[(k4 + t4) * LDB2 + j0 + g], b01 = Bs[(k4 + t4) * LDB2 + j0 + 8 + g];
+                    const double b10 = Bs[(k4 + 4 + t4) * LDB2 + j0 + g], b11 = Bs[(k4 + 4 + t4) * LDB2 + j0 + 8 + g];
+                    dmma884(acc[0][0], acc[0][1], a0, b00);
+                    dmma884(acc[1][0], acc[1][1], a0, b01);
+                    dmma884(acc2[0][0], acc2[0][1], a1, b10);
+                    dmma884(acc2[1][0], acc2[1][1], a1, b11);
+                }
+#pragma unroll
+                for (int nj = 0; nj < 2; ++nj)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) Xs[(j0 + nj * 8 + t4 * 2 + e) * LDX2 + rr] = acc[nj][e] + acc2[nj][e];
+                __syncthreads();
+            }
+            TLP_TICK(2 + 2 * b);
+            {
+                // 16 x 16 diagonal block: four threads per row (row = tid / 4, columns j = 4 jj + q); the finished z_k goes to
+                // the other lanes by a shuffle: 15 steps of (shuffle + FMA, 34 cycles).  One thread per row issues 120 FMAs at
+                // one per 8 cycles, and the compiler orders them as fifteen back-to-back accumulation chains (2 200 cycles).
+                const int row = tid >> 2, q = tid & 3, base = lane & ~3;
+                double z[4], cf[TRB - 1][4];
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) z[jj] = Xs[(j0 + 4 * jj + q) * LDX2 + row];
+#pragma unroll
+                for (int k = 0; k < TRB - 1; ++k)
+#pragma unroll
+                    for (int jj = k >> 2; jj < 4; ++jj) cf[k][jj] = Cd[(j0 + k) * LDCD + 4 * jj + q];      // all up front, off the chain
+#pragma unroll
+                for (int k = 0; k < TRB - 1; ++k) {
+                    const double nz = -__shfl_sync(0xffffffffu, z[k >> 2], base | (k & 3));
+#pragma unroll
+                    for (int jj = k >> 2; jj < 4; ++jj)
+                        if (4 * jj > k || q > k - 4 * jj) z[jj] = fma(nz, cf[k][jj], z[jj]);
+                }
+                const bool valid = row < nr;
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int j = j0 + 4 * jj + q;
+                    const double x = z[jj] * invd[j];
+                    Xs[j * LDX2 + row] = -sgd[j] * x;
+                    if (valid && j < w) X[(int64_t)(kb + j) * ld + r0 + row] = x;
+                }
+            }
+            __syncthreads();
+            TLP_TICK(3 + 2 * b);
+        }
+        if (gidx + 1 < ngrp) {
+            commit(gidx + 1);
+            __syncthreads();
+        }
     }
     if (tid == 0 && half == 0) trace_mark(c, pc.level, 1, true);
 }
@@ -662,6 +758,7 @@ __device__ __forceinline__ void update_tile(const DevCtx& c, const UpdTask& T, d
     const int32_t s = pc.sn;
     if (c.skip && c.skip[s]) return;     // uniform per CTA
     if (threadIdx.x == 0) trace_mark(c, pc.level, cls, false);
+    TLP_TICK(0);
     const int32_t f = c.sn_first[s];
     const int64_t rp = c.sn_rowptr[s];
     const int32_t ld = (int32_t)(c.sn_rowptr[s + 1] - rp);
@@ -715,6 +812,7 @@ __device__ __forceinline__ void update_tile(const DevCtx& c, const UpdTask& T, d
 
     const bool neg = c.has_neg != 0;
     for (int ch = 0; ch < nch; ++ch) {
+        if (ch == 1) TLP_TICK(1);
         cp_async_wait_<UPD_STAGES - 2>();
         __syncthreads();
         const int nx = ch + UPD_STAGES - 1;
@@ -753,6 +851,7 @@ __device__ __forceinline__ void update_tile(const DevCtx& c, const UpdTask& T, d
                     if (atomic) atomicAdd(p, -acc[mi][nj][e]); else *p -= acc[mi][nj][e];
                 }
             }
+    TLP_TICK(2);
     if (threadIdx.x == 0) trace_mark(c, pc.level, cls, true);
 }
 
@@ -795,22 +894,20 @@ static constexpr size_t DF_SMEM = ((size_t)PIECE * LDD + 3 * PIECE + (size_t)NBD
 static constexpr size_t TR_SMEM = ((size_t)PIECE * LDX + (size_t)PIECE * LDLB + (size_t)TRB * LDX + (size_t)TRB * LDLD + TRB) * 8;
 
 static constexpr size_t DF2_SMEM = ((size_t)PIECE * LDC2 + 4 * (size_t)NBD * LDP2 + 3 * PIECE) * 8;
-static constexpr size_t TR2_SMEM = ((size_t)PIECE * LDB2 + (size_t)PIECE * LDX2 + PIECE) * 8;
+static constexpr size_t TR2_SMEM = ((size_t)PIECE * LDB2 + (size_t)PIECE * LDX2 + (size_t)PIECE * LDCD + 2 * PIECE) * 8;
 
-// TLPB200_CHAIN_KERNELS: 0 = round-1 k_diag_factor / k_trsm, 1 = k_diag_factor2 without look-ahead + k_trsm2, 2 (default) = with look-ahead
+// TLPB200_CHAIN_KERNELS: 0 = round-1 k_diag_factor / k_trsm, 1 (default) = k_diag_factor2 / k_trsm2
 static int chain_variant() {
     static const int v = [] {
         const char* e = getenv("TLPB200_CHAIN_KERNELS");
-        return e ? atoi(e) : 2;
+        return e ? atoi(e) : 1;
     }();
     return v;
 }
 
 cudaError_t factor_kernels_static_init() {
     cudaError_t e;
-    e = cudaFuncSetAttribute(k_diag_factor2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DF2_SMEM);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_diag_factor2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DF2_SMEM);
+    e = cudaFuncSetAttribute(k_diag_factor2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DF2_SMEM);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_trsm2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TR2_SMEM);
     if (e != cudaSuccess) return e;
@@ -827,8 +924,7 @@ cudaError_t factor_kernels_static_init() {
 void launch_diag_factor(const DevCtx& c, int32_t begin, int32_t end, cudaStream_t st) {
     if (end <= begin) return;
     const int v = chain_variant();
-    if (v >= 2) k_diag_factor2<true><<<end - begin, DF2_THREADS, DF2_SMEM, st>>>(c, begin);
-    else if (v == 1) k_diag_factor2<false><<<end - begin, DF2_THREADS, DF2_SMEM, st>>>(c, begin);
+    if (v >= 1) k_diag_factor2<<<end - begin, DF2_THREADS, DF2_SMEM, st>>>(c, begin);
     else k_diag_factor<<<end - begin, DF_THREADS, DF_SMEM, st>>>(c, begin);
 }
 void launch_trsm(const DevCtx& c, int32_t begin, int32_t end, cudaStream_t st) {
