@@ -123,7 +123,49 @@ __global__ void k_lat(double* out, unsigned long long* cyc, double seed) {
     out[threadIdx.x] = a + c0 + c1;
 }
 
+// FP64 issue rate: every warp runs 8 independent chains of 64 DFMAs (or DMMAs); nw warps, i.e. nw / 4 per SMSP
+__global__ void k_tput(double* out, unsigned long long* cyc, double seed, int mode) {
+    double v[8], w[8];
+#pragma unroll
+    for (int x = 0; x < 8; ++x) { v[x] = seed + x + threadIdx.x * 1e-3; w[x] = seed - x; }
+    const double b = 1.0 + seed * 1e-9, c = seed * 1e-7;
+    __syncthreads();
+    const unsigned long long t0 = clock64();
+    if (mode == 0) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i)
+#pragma unroll
+            for (int x = 0; x < 8; ++x) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(v[x]) : "d"(b), "d"(c));
+    } else {
+#pragma unroll
+        for (int i = 0; i < 64; ++i)
+#pragma unroll
+            for (int x = 0; x < 8; ++x) dmma884(v[x], w[x], b, c);
+    }
+    const unsigned long long t1 = clock64();
+    __syncthreads();
+    if (threadIdx.x == 0) cyc[0] = t1 - t0;
+    double a = 0;
+#pragma unroll
+    for (int x = 0; x < 8; ++x) a += v[x] + w[x];
+    out[threadIdx.x] = a;
+}
+
 int main() {
+    {
+        double* o; unsigned long long* cy;
+        cudaMalloc(&o, 1024 * 8); cudaMalloc(&cy, 16 * 8);
+        for (int mode = 0; mode < 2; ++mode)
+            for (int nw = 1; nw <= 16; nw *= 2) {
+                k_tput<<<1, 32 * nw>>>(o, cy, 1.000001, mode);
+                cudaDeviceSynchronize();
+                k_tput<<<1, 32 * nw>>>(o, cy, 1.000001, mode);
+                unsigned long long h = 0;
+                cudaMemcpy(&h, cy, 8, cudaMemcpyDeviceToHost);
+                printf("k_tput %s, %2d warps in one CTA: %.2f cycles per instruction per warp (512 independent-chain instructions, warp 0's clock)\n",
+                       mode ? "DMMA" : "DFMA", nw, h / 512.0);
+            }
+    }
     {
         double* o; unsigned long long* cy;
         cudaMalloc(&o, 1024 * 8); cudaMalloc(&cy, 16 * 8);
@@ -218,12 +260,14 @@ int main() {
             cudaEventElapsedTime(&ms, e0, e1); best_t = std::min(best_t, ms);
             if (rep == 5) { char nm[64]; snprintf(nm, 64, "trsm variant %d", variant); ticks(nm, 0, 20); }
             if (variant == 0) {
-                cudaEventRecord(e0);
-                k_update<<<3, UPD_THREADS, UPD_SMEM>>>(c, 0, 1);
-                cudaEventRecord(e1);
-                CK(cudaDeviceSynchronize());
-                cudaEventElapsedTime(&ms, e0, e1);
-                if (rep == 5) { printf("k_update, 3 critical 64x64x128 tiles: %.2f us (CUDA events)\n", ms * 1e3f); ticks("k_update CTA 0", 0, 2); }
+                for (int ks = 1; ks <= 8; ks *= 2) {
+                    cudaEventRecord(e0);
+                    k_update<<<3 * ks, UPD_THREADS, UPD_SMEM>>>(c, 0, 1, ks);
+                    cudaEventRecord(e1);
+                    CK(cudaDeviceSynchronize());
+                    cudaEventElapsedTime(&ms, e0, e1);
+                    if (rep == 5) { printf("k_update, 3 critical 64x64x128 tiles, K split over %d CTAs: %.2f us (CUDA events)\n", ks, ms * 1e3f); ticks("k_update CTA 0", 0, 2); }
+                }
             }
         }
         printf("variant %d: diag %.2f us, trsm %.2f us (CUDA events, best of 6)\n", variant, best_d * 1e3f, best_t * 1e3f);

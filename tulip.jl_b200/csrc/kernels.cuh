@@ -142,7 +142,7 @@ void launch_assemble_k2(const DevCtx& c, const DevMat& A, const double* theta, c
 void launch_small_factor(const DevCtx& c, int32_t begin, int32_t end, size_t smem, cudaStream_t st);
 void launch_diag_factor(const DevCtx& c, int32_t begin, int32_t end, cudaStream_t st);
 void launch_trsm(const DevCtx& c, int32_t begin, int32_t end, cudaStream_t st);
-void launch_update(const DevCtx& c, int32_t begin, int32_t end, int atomic, cudaStream_t st);
+void launch_update(const DevCtx& c, int32_t begin, int32_t end, int atomic, cudaStream_t st, int ksplit = 1);
 void launch_update_lazy(const DevCtx& c, int32_t begin, int32_t end, int32_t* counter, int nsm, int reserve, cudaStream_t st);
 void launch_invert_diag(const DevCtx& c, int32_t begin, int32_t end, cudaStream_t st);   // range of DevCtx::inv_order
 

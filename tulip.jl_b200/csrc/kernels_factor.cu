@@ -11,6 +11,7 @@
 // scripts/dmma_bench.cu); every mma.sync f64 shape lowers to DMMA.8x8x4.  tcgen05 has no FP64 kind.
 #include "kernels.cuh"
 
+#include <algorithm>
 #include <cstdlib>
 
 namespace tlp {
@@ -21,7 +22,7 @@ __device__ unsigned long long g_ticks[2][80];
 #define TLP_TICK(idx)                                                            \
     do {                                                                         \
         if (blockIdx.x == 0 && threadIdx.x == 0) g_ticks[0][idx] = clock64();    \
-        if (blockIdx.x == 0 && threadIdx.x == 128) g_ticks[1][idx] = clock64();  \
+        if (blockIdx.x == 0 && threadIdx.x == 160) g_ticks[1][idx] = clock64();  \
     } while (0)
 #else
 #define TLP_TICK(idx)
@@ -753,7 +754,10 @@ struct UpdShared {
     int32_t next;
 };
 
-__device__ __forceinline__ void update_tile(const DevCtx& c, const UpdTask& T, double* smem_d, UpdShared& sh, int atomic, int cls) {
+// kpart / nparts: this CTA multiplies only its share of the piece's columns (critical tiles are split over several CTAs:
+// a 64x64x128 tile is 14 k cycles on one SM, and the next level's diagonal block waits for it); nparts > 1 needs atomic = 1
+__device__ __forceinline__ void update_tile(const DevCtx& c, const UpdTask& T, double* smem_d, UpdShared& sh, int atomic, int cls,
+                                            int kpart = 0, int nparts = 1) {
     const Piece pc = c.pieces[T.piece];
     const int32_t s = pc.sn;
     if (c.skip && c.skip[s]) return;     // uniform per CTA
@@ -763,8 +767,12 @@ __device__ __forceinline__ void update_tile(const DevCtx& c, const UpdTask& T, d
     const int64_t rp = c.sn_rowptr[s];
     const int32_t ld = (int32_t)(c.sn_rowptr[s + 1] - rp);
     const int32_t* rows = c.sn_rows + rp;
-    const double* panel = c.Lx + c.sn_xptr[s] + (int64_t)(pc.c0 - f) * ld;
-    const int32_t kdim = pc.c1 - pc.c0;
+    const int32_t kall = pc.c1 - pc.c0;
+    const int32_t kshare = ((kall + nparts - 1) / nparts + KC - 1) / KC * KC;      // whole chunks of KC columns per part
+    const int32_t kfirst = kpart * kshare;
+    if (kfirst >= kall) return;      // uniform per CTA
+    const int32_t kdim = min(kshare, kall - kfirst);
+    const double* panel = c.Lx + c.sn_xptr[s] + (int64_t)(pc.c0 - f + kfirst) * ld;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wr = warp >> 1, wc = warp & 1, g = lane >> 2, t4 = lane & 3;
     const int nch = (kdim + KC - 1) / KC;
@@ -802,7 +810,7 @@ __device__ __forceinline__ void update_tile(const DevCtx& c, const UpdTask& T, d
         const int kk = tid - TILE;
         sh.tcol[kk] = (kk < T.nk) ? (int64_t)(rows[T.k0 + kk] - ft) * ldt : 0;
     }
-    if (tid < kdim) sh.sgk[tid] = (double)c.sign[pc.c0 + tid];
+    if (tid < kdim) sh.sgk[tid] = (double)c.sign[pc.c0 + kfirst + tid];
 
     double acc[4][4][2];
 #pragma unroll
@@ -855,11 +863,11 @@ __device__ __forceinline__ void update_tile(const DevCtx& c, const UpdTask& T, d
     if (threadIdx.x == 0) trace_mark(c, pc.level, cls, true);
 }
 
-__global__ void __launch_bounds__(UPD_THREADS, 4) k_update(DevCtx c, int32_t begin, int atomic) {
+__global__ void __launch_bounds__(UPD_THREADS, 4) k_update(DevCtx c, int32_t begin, int atomic, int nparts) {
     extern __shared__ double smem_d[];
     __shared__ UpdShared sh;
-    const UpdTask T = c.upd[begin + blockIdx.x];
-    update_tile(c, T, smem_d, sh, atomic, 2);
+    const UpdTask T = c.upd[begin + blockIdx.x / nparts];
+    update_tile(c, T, smem_d, sh, atomic, 2, blockIdx.x % nparts, nparts);
 }
 
 __global__ void __launch_bounds__(UPD_THREADS, 4) k_update_lazy(DevCtx c, int32_t begin, int32_t end, int32_t* counter,
@@ -932,8 +940,11 @@ void launch_trsm(const DevCtx& c, int32_t begin, int32_t end, cudaStream_t st) {
     if (chain_variant() >= 1) k_trsm2<<<2 * (end - begin), TR2_THREADS, TR2_SMEM, st>>>(c, begin);
     else k_trsm<<<end - begin, TR_THREADS, TR_SMEM, st>>>(c, begin);
 }
-void launch_update(const DevCtx& c, int32_t begin, int32_t end, int atomic, cudaStream_t st) {
-    if (end > begin) k_update<<<end - begin, UPD_THREADS, UPD_SMEM, st>>>(c, begin, atomic);
+// ksplit > 1 (critical tiles, atomic accumulation): each tile's K range is shared by ksplit CTAs
+void launch_update(const DevCtx& c, int32_t begin, int32_t end, int atomic, cudaStream_t st, int ksplit) {
+    if (end <= begin) return;
+    const int np = atomic ? std::max(1, ksplit) : 1;
+    k_update<<<(end - begin) * np, UPD_THREADS, UPD_SMEM, st>>>(c, begin, atomic, np);
 }
 // persistent work-queue launch: `nsm` SMs x 4 resident CTAs; CTAs on SMs >= nsm - reserve exit immediately
 void launch_update_lazy(const DevCtx& c, int32_t begin, int32_t end, int32_t* counter, int nsm, int reserve, cudaStream_t st) {

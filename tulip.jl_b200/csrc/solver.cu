@@ -459,7 +459,7 @@ void enqueue_factor(tlpb200_solver* s, int64_t& count) {
             CK(cudaStreamWaitEvent(s->aux_stream, s->ev_f[l], 0));
             if (has_work(s, tlpb200_solver::WL_EXT, lp.ext_crit_end, lp.ext_end)) { launch_update((*s->cur), lp.ext_crit_end, lp.ext_end, 1, s->aux_stream); count++; }
             CK(cudaEventRecord(s->ev_ur[l], s->aux_stream));
-            if (has_work(s, tlpb200_solver::WL_EXT, lp.ext_begin, lp.ext_crit_end)) { launch_update((*s->cur), lp.ext_begin, lp.ext_crit_end, 1, st); count++; }
+            if (has_work(s, tlpb200_solver::WL_EXT, lp.ext_begin, lp.ext_crit_end)) { launch_update((*s->cur), lp.ext_begin, lp.ext_crit_end, 1, st, s->crit_ksplit); count++; }
         }
     }
     if (overlap && s->split_chain && nlev > 0) CK(cudaStreamWaitEvent(st, s->ev_ur[nlev - 1], 0));
@@ -853,6 +853,7 @@ void setup_device(tlpb200_solver* s) {
         for (auto& x : s->side2) CK(cudaStreamCreateWithPriority(&x, cudaStreamNonBlocking, lo));
         CK(cudaStreamCreateWithPriority(&s->aux_stream, cudaStreamNonBlocking, std::min(lo, hi + 1)));
         if (const char* e = getenv("TLPB200_SPLIT_CHAIN")) s->split_chain = atoi(e) != 0;
+        if (const char* e = getenv("TLPB200_CRIT_KSPLIT")) s->crit_ksplit = std::max(1, std::min(8, atoi(e)));
         if (const char* e = getenv("TLPB200_PACK_SPLIT")) s->pack_split = atof(e);
         if (const char* e = getenv("TLPB200_PACK_SLICE")) s->pack_slice = std::max(1, atoi(e));
         CK(cudaEventCreateWithFlags(&s->ev_pack, cudaEventDisableTiming));

@@ -38,6 +38,7 @@ struct tlpb200_solver {
     std::vector<cudaEvent_t> ev_d, ev_tr, ev_ur;   // per level: diagonal blocks done / rest of the trsm done / rest of the urgent tiles done
     cudaStream_t aux_stream = nullptr;        // non-critical part of the chain kernels (TLPB200_SPLIT_CHAIN)
     bool split_chain = true;
+    int crit_ksplit = 4;          // CTAs per critical update tile (K range shared, RED accumulation; TLPB200_CRIT_KSPLIT)
     cudaEvent_t ev_pack = nullptr;
     std::vector<cudaEvent_t> ev_stage;   // one event per 256 KiB chunk of a device -> host result copy (pipelined staging)
     int pack_slice = 96;          // TLPB200_PACK_SLICE: repack tiles issued per level from the split level on
