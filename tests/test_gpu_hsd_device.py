@@ -62,10 +62,11 @@ def test_device_iterate_stepwise_equals_host_iterates():
         assert d.iterate() == "Trm_Unknown"
         pt = d.point()
         x, y, zl, tau, kappa = snaps[k]
-        np.testing.assert_allclose(pt["x"], x, rtol=1e-9, atol=1e-11)
-        np.testing.assert_allclose(pt["y"], y, rtol=1e-9, atol=1e-11)
-        np.testing.assert_allclose(pt["zl"], zl, rtol=1e-9, atol=1e-11)
-        assert abs(pt["tau"] - tau) <= 1e-10 * abs(tau) and abs(pt["kappa"] - kappa) <= 1e-10 * max(abs(kappa), 1e-3)
+        # two solver handles = two factorisations per step (atomic accumulation order differs): equal to O(kappa u), not bitwise
+        np.testing.assert_allclose(pt["x"], x, rtol=1e-8, atol=1e-10)
+        np.testing.assert_allclose(pt["y"], y, rtol=1e-8, atol=1e-10)
+        np.testing.assert_allclose(pt["zl"], zl, rtol=1e-8, atol=1e-10)
+        assert abs(pt["tau"] - tau) <= 1e-9 * abs(tau) and abs(pt["kappa"] - kappa) <= 1e-9 * max(abs(kappa), 1e-3)
 
 
 @pytest.mark.parametrize("name", list(LPEX))

@@ -270,8 +270,10 @@ def test_multi_rhs_and_device_pointer_api():
         ddx = torch.zeros(n, dtype=torch.float64, device=dev); ddy = torch.zeros(m, dtype=torch.float64, device=dev)
         k.solve_dev(ddx, ddy, t(XP[0]), t(XD[0]))
         torch.cuda.synchronize()
-        np.testing.assert_allclose(ddx.cpu().numpy(), DX[0], rtol=1e-9, atol=1e-12)
-        np.testing.assert_allclose(ddy.cpu().numpy(), DY[0], rtol=1e-9, atol=1e-12)
+        # a second factorisation of the same data: update tiles reach the ancestors through RED.ADD.F64 (and the critical tiles
+        # are split over K across CTAs), so two factors differ by summation order -- O(kappa u) in the solution, not bitwise
+        np.testing.assert_allclose(ddx.cpu().numpy(), DX[0], rtol=1e-7, atol=1e-10)
+        np.testing.assert_allclose(ddy.cpu().numpy(), DY[0], rtol=1e-7, atol=1e-10)
 
 
 def test_graph_and_plain_launch_agree():
@@ -290,7 +292,8 @@ def test_graph_and_plain_launch_agree():
         out.append(np.concatenate([dx, dy]))
         st = k.stats()
         assert st["launches_update"] > 0 and st["launches_solve"] > 0
-    np.testing.assert_allclose(out[0], out[1], rtol=1e-9, atol=1e-12)
+    # two factorisations (atomic accumulation order differs from run to run): equal to O(kappa u), theta spans e^-4 .. e^4
+    np.testing.assert_allclose(out[0], out[1], rtol=1e-7, atol=1e-10)
 
 
 def test_empty_and_ragged_inputs():
