@@ -148,3 +148,74 @@ def trsm3(L11, sign, A21):
                 x=z[j]*invd[j0+j]; Xs[(j0+j)*LDX2+tid]=-sgd[j0+j]*x
                 if tid<nr and j0+j<w: out[tid,j0+j]=x
     return out
+
+
+# ---- k_invert_diag2 (tulip.jl_b200/csrc/kernels.cu): block-doubling inverse of a 128x128 lower-triangular block ----
+LDI2 = 132; LDT2 = 68
+
+
+def _inv2_tiles(Cs, Tb, TPW, second, h, p, mi, nj0):
+    a0 = 2 * p * h; c0 = a0 + h
+    acc = [[[0.0] * 32, [0.0] * 32] for _ in range(TPW)]
+    kbeg = 0 if second else 8 * nj0
+    kend = 8 * (mi + 1) if second else h
+    for k0 in range(kbeg, kend, 4):
+        if second:
+            a = [Cs[(c0 + k0 + (l & 3)) * LDI2 + c0 + 8 * mi + (l >> 2)] for l in L]
+        else:
+            a = [Cs[(a0 + k0 + (l & 3)) * LDI2 + c0 + 8 * mi + (l >> 2)] for l in L]
+        for x in range(TPW):
+            nj = nj0 + x
+            if second:
+                b = [Tb[(p * h + 8 * nj + (l >> 2)) * LDT2 + k0 + (l & 3)] for l in L]
+            else:
+                b = [Cs[(a0 + 8 * nj + (l >> 2)) * LDI2 + a0 + k0 + (l & 3)] for l in L]
+            dmma(a, b, acc[x][0], acc[x][1])
+    out = []
+    for x in range(TPW):
+        nj = nj0 + x
+        for e in range(2):
+            for l in L:
+                g, t4 = l >> 2, l & 3
+                if second:
+                    out.append(('C', (a0 + 8 * nj + 2 * t4 + e) * LDI2 + c0 + 8 * mi + g, -acc[x][e][l]))
+                else:
+                    out.append(('T', (p * h + 8 * nj + 2 * t4 + e) * LDT2 + 8 * mi + g, acc[x][e][l]))
+    return out
+
+
+def invert2(Lm):
+    """mirror of k_invert_diag2 up to the inverse in shared memory; returns X = L^-1 (nb x nb)"""
+    nb = Lm.shape[0]
+    Cs = np.full(128 * LDI2, 1e300); Tb = np.full(64 * LDT2, 1e300); rdiag = np.zeros(128)
+    for k in range(128):
+        for il in range(128):
+            Cs[k * LDI2 + il] = Lm[il, k] if (k < nb and il < nb and il >= k) else (1.0 if (k == il and k >= nb) else 0.0)
+    for t in range(128): rdiag[t] = 1.0 / Cs[t * LDI2 + t]
+    for t in range(128):
+        d0 = t & ~15; cc = t & 15; x = [0.0] * 16
+        for i in range(16):
+            a = 1.0 if i == cc else 0.0
+            for k in range(i): a = -Cs[(d0 + k) * LDI2 + d0 + i] * x[k] + a
+            x[i] = a * rdiag[d0 + i]
+        for i in range(16): Tb[t * 16 + i] = x[i]
+    for t in range(128):
+        d0 = t & ~15
+        for i in range(16): Cs[t * LDI2 + d0 + i] = Tb[t * 16 + i]
+    for h in (16, 32, 64):
+        TPW = h // 16; WPP = h // 4
+        for second in (False, True):
+            writes = []
+            for warp in range(16):
+                p = warp // WPP; widx = warp % WPP
+                writes += _inv2_tiles(Cs, Tb, TPW, second, h, p, widx >> 1, (widx & 1) * TPW)
+            seen = set()
+            for kind, addr, val in writes:      # applied after the phase: the barrier
+                assert (kind, addr) not in seen; seen.add((kind, addr))
+                (Cs if kind == 'C' else Tb)[addr] = val
+    X = np.zeros((nb, nb))
+    for cc in range(nb):
+        for r in range(cc, nb): X[r, cc] = Cs[cc * LDI2 + r]
+    upper = max((abs(Cs[cc * LDI2 + r]) for cc in range(128) for r in range(cc)), default=0.0)
+    assert upper == 0.0      # the outputs rely on a zero upper triangle
+    return X

@@ -47,3 +47,14 @@ def test_trsm_mirror_matches_a_dense_solve(w, nr, signed):
     X = ce.trsm3(L0, sign, A)
     ref = np.linalg.solve(L0, A.T).T @ np.diag(sign)
     assert np.abs(X - ref).max() <= 1e-9 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("nb", [1, 5, 16, 17, 100, 128])
+def test_block_doubling_inverse_mirror(nb):
+    """k_invert_diag2: 16x16 substitution + three levels of DMMA block doubling; every output entry written once per phase,
+    upper triangle exactly zero (asserted inside the mirror)"""
+    rng = np.random.default_rng(300 + nb)
+    L = np.tril(rng.standard_normal((nb, nb))) * 0.3
+    L[np.diag_indices(nb)] = 1 + rng.random(nb)
+    X = ce.invert2(L)
+    assert np.abs(X @ L - np.eye(nb)).max() <= 1e-12

@@ -11,6 +11,7 @@
 #include "kernels.cuh"
 
 #include <climits>
+#include <cstdlib>
 
 namespace tlp {
 
@@ -229,6 +230,168 @@ __global__ void __launch_bounds__(INV_THREADS) k_invert_diag(DevCtx c, int32_t b
     for (int e = tid; e < SBLK * SBLK; e += INV_THREADS) {
         const int rr = e / SBLK, cc = e % SBLK;
         sub[rr * SBLK + cc] = Cs[cc * LDI + rr];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_invert_diag2 (round 2): the same three outputs (Dinv, DinvT, LsubT) with the inverse built by block doubling on the FP64
+// tensor pipe.  k_invert_diag lets thread i run a dependent dot product of length i - j for every column j (8 128 chained
+// FMAs for the last row, two barriers per column): 270 us per block, 1.4 ms of config 4's 8.3 ms update!.  Here:
+//   1. the eight 16x16 diagonal blocks by substitution, one thread per column (128 threads, reciprocal diagonal precomputed);
+//   2. for h = 16, 32, 64: L = [A 0; B C] with A^-1, C^-1 known  ->  T = B A^-1, X21 = -C^-1 T, both as DMMA 8x8x4 tile
+//      products out of shared memory (operands column-major, leading dimension 132: conflict-free fragments), zero tiles of
+//      the triangular factors skipped; 3 x 2 barriers instead of 256;
+//   3. Dinv with 16-byte stores, DinvT through a 128 x 32 staging buffer of odd stride (no bank conflicts on the transposed
+//      read), LsubT as before.
+// ------------------------------------------------------------------------------------------
+constexpr int INV2_THREADS = 512;
+constexpr int LDI2 = SBLK + 4;      // 132
+constexpr int LDT2 = 68;            // T = B A^-1, at most 64 x 64
+constexpr int LDS2 = 33;            // transposition staging [128][33]
+
+// tiles (mi, nj0 .. nj0 + TPW - 1) of pair p at level h: GEMM 1 (T = B A^-1) or GEMM 2 (X21 = -C^-1 T)
+template <int TPW, bool SECOND>
+__device__ __forceinline__ void inv2_tiles(double* Cs, double* Tb, int h, int p, int mi, int nj0, int g, int t4) {
+    const int a0 = 2 * p * h, c0 = a0 + h;      // first row / column of A and of C
+    double acc[TPW][2];
+#pragma unroll
+    for (int x = 0; x < TPW; ++x) acc[x][0] = acc[x][1] = 0.0;
+    // GEMM 1: A^-1 is lower triangular: rows k < 8 nj of its column tile nj are zero.  GEMM 2: C^-1 lower: columns k >= 8 (mi + 1)
+    // of its row tile mi are zero.
+    const int kbeg = SECOND ? 0 : 8 * nj0, kend = SECOND ? 8 * (mi + 1) : h;
+    for (int k0 = kbeg; k0 < kend; k0 += 4) {
+        const double a = SECOND ? Cs[(c0 + k0 + t4) * LDI2 + c0 + 8 * mi + g]      // C^-1[row, k]
+                                : Cs[(a0 + k0 + t4) * LDI2 + c0 + 8 * mi + g];     // B[row, k]
+#pragma unroll
+        for (int x = 0; x < TPW; ++x) {
+            const int nj = nj0 + x;
+            const double b = SECOND ? Tb[(p * h + 8 * nj + g) * LDT2 + k0 + t4]          // T[k, n]
+                                    : Cs[(a0 + 8 * nj + g) * LDI2 + a0 + k0 + t4];       // A^-1[k, n]
+            dmma884(acc[x][0], acc[x][1], a, b);
+        }
+    }
+#pragma unroll
+    for (int x = 0; x < TPW; ++x) {
+        const int nj = nj0 + x;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            if (SECOND) Cs[(a0 + 8 * nj + 2 * t4 + e) * LDI2 + c0 + 8 * mi + g] = -acc[x][e];      // over B, which GEMM 1 has consumed
+            else Tb[(p * h + 8 * nj + 2 * t4 + e) * LDT2 + 8 * mi + g] = acc[x][e];
+        }
+    }
+}
+
+template <int H>
+__device__ __forceinline__ void inv2_level(double* Cs, double* Tb, int warp, int g, int t4) {
+    constexpr int TPW = H / 16;               // tiles per warp: 16 warps share 64 / H pairs x (H / 8)^2 tiles
+    constexpr int WPP = H / 4;                // warps per pair
+    const int p = warp / WPP, widx = warp % WPP;
+    const int mi = widx >> 1, nj0 = (widx & 1) * TPW;
+    inv2_tiles<TPW, false>(Cs, Tb, H, p, mi, nj0, g, t4);
+    __syncthreads();
+    inv2_tiles<TPW, true>(Cs, Tb, H, p, mi, nj0, g, t4);
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(INV2_THREADS, 1) k_invert_diag2(DevCtx c, int32_t begin) {
+    extern __shared__ double smem_d[];
+    double* Cs = smem_d;                      // [SBLK][LDI2] column-major: L on entry, X = L^{-1} on exit (upper part zero)
+    double* Tb = Cs + SBLK * LDI2;            // [64][LDT2] / [128][16] / [128][LDS2] scratch
+    double* rdiag = Tb + 64 * LDT2;           // [SBLK]
+    const int32_t b = c.inv_order[begin + blockIdx.x];
+    const int32_t s = c.dblk_sn[b], bi = c.dblk_idx[b];
+    if (c.skip && c.skip[s]) return;
+    const int32_t f = c.sn_first[s];
+    const int32_t nc = c.sn_first[s + 1] - f;
+    const int32_t ld = (int32_t)(c.sn_rowptr[s + 1] - c.sn_rowptr[s]);
+    const int32_t lc0 = bi * SBLK, nb = min(SBLK, nc - lc0);
+    const double* D = c.Lx + c.sn_xptr[s] + (int64_t)lc0 * ld + lc0;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t4 = lane & 3;
+    const int il = tid & (SBLK - 1), q4 = tid >> 7;
+    // lower triangle in; zero above it; identity on the padding rows / columns (nb < 128)
+    for (int kb = 0; kb < SBLK; kb += 64) {
+        double v[16];
+#pragma unroll
+        for (int x = 0; x < 16; ++x) {
+            const int k = kb + q4 + 4 * x;
+            v[x] = (k < nb && il < nb && il >= k) ? D[(int64_t)k * ld + il] : ((k == il && k >= nb) ? 1.0 : 0.0);
+        }
+#pragma unroll
+        for (int x = 0; x < 16; ++x) Cs[(kb + q4 + 4 * x) * LDI2 + il] = v[x];
+    }
+    __syncthreads();
+    if (tid < SBLK) rdiag[tid] = 1.0 / Cs[tid * LDI2 + tid];
+    __syncthreads();
+    // 1. 16x16 diagonal blocks: thread t = column t of the block inverse, x_i = (delta_ic - sum_{k<i} L_ik x_k) / L_ii
+    if (tid < SBLK) {
+        const int d0 = tid & ~15, cc = tid & 15;
+        double x[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            double a = (i == cc) ? 1.0 : 0.0;
+#pragma unroll
+            for (int k = 0; k < i; ++k) a = fma(-Cs[(d0 + k) * LDI2 + d0 + i], x[k], a);
+            x[i] = a * rdiag[d0 + i];
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) Tb[tid * 16 + i] = x[i];
+    }
+    __syncthreads();
+    if (tid < SBLK) {
+        const int d0 = tid & ~15;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) Cs[tid * LDI2 + d0 + i] = Tb[tid * 16 + i];
+    }
+    __syncthreads();
+    // 2. block doubling
+    inv2_level<16>(Cs, Tb, warp, g, t4);
+    inv2_level<32>(Cs, Tb, warp, g, t4);
+    inv2_level<64>(Cs, Tb, warp, g, t4);
+    // 3. outputs.  Dinv (column cc, row r), 16-byte stores
+    double* out = c.Dinv + (int64_t)b * SBLK * SBLK;
+    double* outT = c.DinvT + (int64_t)b * SBLK * SBLK;
+    for (int e = tid; e < SBLK * SBLK / 2; e += INV2_THREADS) {
+        const int cc = e >> 6, r = (e & 63) * 2;
+        const double2 v = *reinterpret_cast<const double2*>(Cs + cc * LDI2 + r);
+        double2 o;
+        o.x = (cc < nb && r < nb && r >= cc) ? v.x : 0.0;
+        o.y = (cc < nb && r + 1 < nb && r + 1 >= cc) ? v.y : 0.0;
+        *reinterpret_cast<double2*>(out + cc * SBLK + r) = o;
+    }
+    // DinvT (column r, row cc) = X[r, cc]: 32 columns cc at a time through Tb[r][LDS2]
+    for (int cb = 0; cb < SBLK; cb += 32) {
+        __syncthreads();
+        for (int e = tid; e < 32 * SBLK; e += INV2_THREADS) {
+            const int cc = cb + (e >> 7), r = e & (SBLK - 1);
+            Tb[r * LDS2 + (cc - cb)] = (cc < nb && r < nb && r >= cc) ? Cs[cc * LDI2 + r] : 0.0;
+        }
+        __syncthreads();
+        for (int e = tid; e < 32 * SBLK; e += INV2_THREADS) {
+            const int r = e >> 5, j = e & 31;
+            outT[r * SBLK + cb + j] = Tb[r * LDS2 + j];
+        }
+    }
+    // transposed copy of the sub-diagonal tile L[(bi+1) block rows, bi block cols] for the backward sweep:
+    // LsubT[b][rr * 128 + cc] = L[lc0 + 128 + rr, lc0 + cc]; Cs is reused as [128][129]
+    __syncthreads();
+    constexpr int LDO = SBLK + 1;
+    double* sub = c.LsubT + (int64_t)b * SBLK * SBLK;
+    const int32_t nbn = min(SBLK, nc - (lc0 + SBLK));       // rows of the next diagonal block (<= 0: none)
+    const double* Lsub = c.Lx + c.sn_xptr[s] + (int64_t)lc0 * ld + lc0 + SBLK;
+    for (int kb = 0; kb < SBLK; kb += 64) {
+        double v[16];
+#pragma unroll
+        for (int x = 0; x < 16; ++x) {
+            const int cc = kb + q4 + 4 * x;
+            v[x] = (il < nbn && cc < nb) ? Lsub[(int64_t)cc * ld + il] : 0.0;
+        }
+#pragma unroll
+        for (int x = 0; x < 16; ++x) Cs[(kb + q4 + 4 * x) * LDO + il] = v[x];
+    }
+    __syncthreads();
+    for (int e = tid; e < SBLK * SBLK; e += INV2_THREADS) {
+        const int rr = e / SBLK, cc = e % SBLK;
+        sub[rr * SBLK + cc] = Cs[cc * LDO + rr];
     }
 }
 
@@ -715,6 +878,7 @@ size_t small_factor_smem(int32_t max_elems, int32_t max_nrow) {
 }
 
 static constexpr size_t INV_SMEM = (size_t)SBLK * (SBLK + 1) * 8;
+static constexpr size_t INV2_SMEM = ((size_t)SBLK * LDI2 + 64 * LDT2 + SBLK) * 8;
 static constexpr size_t SL_SMEM = ((size_t)SBLK * SBLK + SBLK + (size_t)SL_CG * SBLK) * 8;
 
 #define SETATTR(k, bytes)                                                                                   \
@@ -726,6 +890,7 @@ static constexpr size_t SL_SMEM = ((size_t)SBLK * SBLK + SBLK + (size_t)SL_CG * 
 cudaError_t kernels_static_init() {
     SETATTR(k_small_factor, 96 * 1024);
     SETATTR(k_invert_diag, INV_SMEM);
+    SETATTR(k_invert_diag2, INV2_SMEM);
     SETATTR(k_fwd_large, SL_SMEM);
     SETATTR(k_bwd_large, SL_SMEM);
     return factor_kernels_static_init();
@@ -734,8 +899,12 @@ cudaError_t kernels_static_init() {
 void launch_small_factor(const DevCtx& c, int32_t begin, int32_t end, size_t smem, cudaStream_t st) {
     if (end > begin) k_small_factor<<<end - begin, SMALL_THREADS, smem, st>>>(c, begin);
 }
+// TLPB200_INVERT_KERNEL=0: round-1 k_invert_diag
 void launch_invert_diag(const DevCtx& c, int32_t begin, int32_t end, cudaStream_t st) {
-    if (end > begin) k_invert_diag<<<end - begin, INV_THREADS, INV_SMEM, st>>>(c, begin);
+    static const bool old_kernel = [] { const char* e = getenv("TLPB200_INVERT_KERNEL"); return e && atoi(e) == 0; }();
+    if (end <= begin) return;
+    if (old_kernel) k_invert_diag<<<end - begin, INV_THREADS, INV_SMEM, st>>>(c, begin);
+    else k_invert_diag2<<<end - begin, INV2_THREADS, INV2_SMEM, st>>>(c, begin);
 }
 void launch_fwd_small(const DevCtx& c, int32_t begin, int32_t end, cudaStream_t st) {
     if (end > begin) k_fwd_small<<<nblk(end - begin, SOLVE_SMALL_WARPS), 32 * SOLVE_SMALL_WARPS, 0, st>>>(c, begin, end);
